@@ -1,0 +1,637 @@
+// hank_api.cu — context management and the C ABI of include/hankb200.h.
+// Reference functions replaced are cited in the header next to each declaration.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+#include "hank_ctx.h"
+#include "../../include/hankb200.h"
+
+namespace hank {
+
+int set_error(hank_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+int cuda_check(hank_ctx* c, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return HANK_OK;
+  return set_error(c, HANK_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CK(call)                                                   \
+  do {                                                             \
+    int rc__ = hank::cuda_check(c, (call), #call);                 \
+    if (rc__) return rc__;                                         \
+  } while (0)
+#define RC(call)                 \
+  do {                           \
+    int rc__ = (call);           \
+    if (rc__) return rc__;       \
+  } while (0)
+
+// ---- small kernels ---------------------------------------------------------------------
+__global__ void k_extract_rw(const double* __restrict__ x, int P, double* r, double* w) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < P) { r[t] = x[4 * t + 2]; w[t] = x[4 * t + 3]; }
+}
+// V: n x K column-major (lane-major); dr, dw: [K][P]
+__global__ void k_extract_drdw(const double* __restrict__ V, int P, int K, double* dr, double* dw) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < K * P) {
+    int l = i / P, t = i - l * P;
+    const double* v = V + (size_t)l * 4 * P;
+    dr[i] = v[4 * t + 2]; dw[i] = v[4 * t + 3];
+  }
+}
+__global__ void k_reduce_partials(const double* __restrict__ part, int NW, int count, double* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) {
+    double s = 0.0;
+    for (int w = 0; w < NW; ++w) s += part[(size_t)i * NW + w];
+    out[i] = s;
+  }
+}
+// Compiled KS residuals (KrusellSmith.yaml:90-94; ModelParser.jl:217-259), equation-fastest.
+__global__ void k_ks_residual(int P, double alpha, double delta, double ssKS, const double* __restrict__ x,
+                              const double* __restrict__ KD, const double* __restrict__ Z, double* F) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P) return;
+  const double Y = x[4 * t], KS = x[4 * t + 1], r = x[4 * t + 2], w = x[4 * t + 3];
+  const double Kl = t == 0 ? ssKS : x[4 * (t - 1) + 1];
+  const double Ka = pow(Kl, alpha), Ka1 = pow(Kl, alpha - 1.0);
+  F[4 * t + 0] = Y - (Z[t] * Ka);
+  F[4 * t + 1] = (r + delta) - ((alpha * Z[t]) * Ka1);
+  F[4 * t + 2] = w - (((1.0 - alpha) * Z[t]) * Ka);
+  F[4 * t + 3] = KS - KD[t];
+}
+// Tangent lanes of the residuals: JV[:, l] for V[:, l] and K̇D[l] (dKD: [K][P]).
+__global__ void k_ks_residual_tangent(int P, int K, double alpha, double ssKS, const double* __restrict__ x,
+                                      const double* __restrict__ Z, const double* __restrict__ V,
+                                      const double* __restrict__ dKD, double* JV) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K * P) return;
+  const int l = i / P, t = i - l * P;
+  const double Kl = t == 0 ? ssKS : x[4 * (t - 1) + 1];
+  const double Ka1 = pow(Kl, alpha - 1.0), Ka2 = pow(Kl, alpha - 2.0);
+  const double* d = V + (size_t)l * 4 * P;
+  const double dKl = t == 0 ? 0.0 : d[4 * (t - 1) + 1];
+  const double dKa = dKl * alpha * Ka1, dKa1 = dKl * (alpha - 1.0) * Ka2;
+  double* o = JV + (size_t)l * 4 * P;
+  o[4 * t + 0] = d[4 * t + 0] - (Z[t] * dKa);
+  o[4 * t + 1] = d[4 * t + 2] - ((alpha * Z[t]) * dKa1);
+  o[4 * t + 2] = d[4 * t + 3] - (((1.0 - alpha) * Z[t]) * dKa);
+  o[4 * t + 3] = d[4 * t + 1] - dKD[(size_t)l * P + t];
+}
+// Unit seeds for Jacobian columns: lane l perturbs r or w (v = 2, 3) at period tcol.
+__global__ void k_unit_seeds(int P, int K, const int* __restrict__ lane_col, double* dr, double* dw) {
+  int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= K) return;
+  const int col = lane_col[l], t = col >> 2, v = col & 3;
+  if (v == 2) dr[(size_t)l * P + t] = 1.0;
+  if (v == 3) dw[(size_t)l * P + t] = 1.0;
+}
+// Jacobian columns with unit seeds e_col: direct residual terms + household term −K̇D.
+__global__ void k_ks_jac_columns(int P, int col_begin, int ncols, double alpha, double ssKS,
+                                 const double* __restrict__ x, const double* __restrict__ Z,
+                                 const int* __restrict__ col_lane, const double* __restrict__ dKD, double* J) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncols * P) return;
+  const int c = i / P, t = i - c * P;
+  const int col = col_begin + c, tc = col >> 2, v = col & 3;
+  double* o = J + (size_t)c * 4 * P;
+  double o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+  if (t == tc) { if (v == 0) o0 = 1.0; if (v == 2) o1 = 1.0; if (v == 3) o2 = 1.0; if (v == 1) o3 = 1.0; }
+  if (v == 1 && t == tc + 1) {  // KS(-1) terms
+    const double Kl = x[4 * tc + 1];
+    const double Ka1 = pow(Kl, alpha - 1.0), Ka2 = pow(Kl, alpha - 2.0);
+    const double dKa = 1.0 * alpha * Ka1, dKa1 = 1.0 * (alpha - 1.0) * Ka2;
+    o0 = 0.0 - (Z[t] * dKa); o1 = 0.0 - ((alpha * Z[t]) * dKa1); o2 = 0.0 - (((1.0 - alpha) * Z[t]) * dKa);
+  }
+  const int l = col_lane[c];
+  if (l >= 0) o3 -= dKD[(size_t)l * P + t];
+  o[4 * t + 0] = o0; o[4 * t + 1] = o1; o[4 * t + 2] = o2; o[4 * t + 3] = o3;
+  (void)ssKS;
+}
+// make_endogenous_transition's bracket rule (ForwardIteration.jl:46-75).
+__global__ void k_lottery(const double* __restrict__ grid, int n_a, int G, const double* __restrict__ pol,
+                          int32_t* m_out, double* om_out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G) return;
+  const double p = pol[i];
+  const int m = lower_bound(grid, n_a, p) + 1;
+  double om = 1.0;
+  if (m > 1 && m <= n_a) om = (p - grid[m - 2]) / (grid[m - 1] - grid[m - 2]);
+  m_out[i] = m;
+  if (om_out) om_out[i] = om;
+}
+
+// ---- n_e dispatch ----------------------------------------------------------------------
+#define NE_DISPATCH(c, CALL)                                                              \
+  switch ((c)->n_e) {                                                                     \
+    case 3: return Sweeps<3>::CALL;                                                       \
+    case 7: return Sweeps<7>::CALL;                                                       \
+    case 11: return Sweeps<11>::CALL;                                                     \
+    default: return set_error(c, HANK_ERR_ARG, "n_e must be one of 3, 7, 11 in this build"); \
+  }
+static int sw_backward_primal(hank_ctx* c, int P, const double* vT, const double* r, const double* w) {
+  NE_DISPATCH(c, backward_primal(c, P, vT, r, w));
+}
+static int sw_backward_tangent(hank_ctx* c, int P, int K, const double* dr, const double* dw,
+                               const double* dvalT, double* dpol, double* dvf) {
+  NE_DISPATCH(c, backward_tangent(c, P, K, dr, dw, dvalT, dpol, dvf));
+}
+static int sw_forward_primal(hank_ctx* c, int P, const double* D0, const double* pol, double* KD) {
+  NE_DISPATCH(c, forward_primal(c, P, D0, pol, KD));
+}
+static int sw_forward_tangent(hank_ctx* c, int P, int K, const double* pol, const double* dpol,
+                              double* dkdpart, int* nw) {
+  NE_DISPATCH(c, forward_tangent(c, P, K, pol, dpol, dkdpart, nw));
+}
+
+template <typename T>
+static int dalloc(hank_ctx* c, T** p, size_t count) {
+  return cuda_check(c, cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)), "cudaMalloc");
+}
+template <typename T>
+static void dfree(T*& p) { if (p) cudaFree(p); p = nullptr; }
+
+static int check_status(hank_ctx* c) {
+  CK(cudaMemcpyAsync(c->h_status, c->d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  const int code = c->h_status[0];
+  if (code == 0) return HANK_OK;
+  const int a = c->h_status[1], e = c->h_status[2], t = c->h_status[3];
+  CK(cudaMemsetAsync(c->d_status, 0, 4 * sizeof(int), c->stream));
+  char buf[256];
+  const char* what = code == HANK_ERR_DOMAIN ? "DomainError: negative base under a non-integer power"
+                   : code == HANK_ERR_KNOTS ? "knot-vectors must be unique and sorted in increasing order"
+                   : code == HANK_ERR_NONMONOTONE ? "policy is not monotone in a (gather lottery not applicable)"
+                   : "device-side failure";
+  snprintf(buf, sizeof buf, "%s at period t=%d, a=%d, e=%d", what, t, a, e);
+  return set_error(c, code, buf);
+}
+
+static int ensure_lanes(hank_ctx* c, int K) {
+  if (K <= c->Kcap) return HANK_OK;
+  const size_t per_lane = (size_t)c->P_alloc * c->Gp * sizeof(double);
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  const size_t have = (size_t)c->Kcap * per_lane;
+  int Kmax = (int)std::min<size_t>((size_t)K, (size_t)(0.85 * (double)(free_b + have)) / per_lane);
+  if (Kmax < 1) return set_error(c, HANK_ERR_CUDA, "not enough device memory for one tangent lane");
+  if (Kmax <= c->Kcap) return HANK_OK;
+  dfree(c->d_dr); dfree(c->d_dw); dfree(c->d_dpol); dfree(c->d_dkdpart); dfree(c->d_dKD);
+  c->Kcap = 0;
+  RC(dalloc(c, &c->d_dr, (size_t)Kmax * c->P_alloc));
+  RC(dalloc(c, &c->d_dw, (size_t)Kmax * c->P_alloc));
+  RC(dalloc(c, &c->d_dpol, (size_t)Kmax * c->P_alloc * c->Gp));
+  CK(cudaMemsetAsync(c->d_dpol, 0, (size_t)Kmax * c->P_alloc * c->Gp * sizeof(double), c->stream));
+  RC(dalloc(c, &c->d_dkdpart, (size_t)Kmax * c->P_alloc * 16));
+  RC(dalloc(c, &c->d_dKD, (size_t)Kmax * c->P_alloc));
+  c->Kcap = Kmax;
+  return HANK_OK;
+}
+static int ensure_V(hank_ctx* c, int K) {
+  if (K <= c->Vcap) return HANK_OK;
+  dfree(c->d_V); dfree(c->d_JV);
+  c->Vcap = 0;
+  const size_t n = (size_t)4 * c->P;
+  RC(dalloc(c, &c->d_V, n * K));
+  RC(dalloc(c, &c->d_JV, n * K));
+  c->Vcap = K;
+  return HANK_OK;
+}
+
+static inline int nblk(size_t n, int b = 256) { return (int)((n + b - 1) / b); }
+
+// Copies `rows` columns of n_a doubles between the caller's dense [rows][n_a] layout and the
+// device's padded [rows][lda] layout.
+static int copy_in(hank_ctx* c, double* dst_padded, const double* src_dense, size_t rows) {
+  return cuda_check(c, cudaMemcpy2DAsync(dst_padded, (size_t)c->lda * 8, src_dense, (size_t)c->n_a * 8,
+                                         (size_t)c->n_a * 8, rows, cudaMemcpyDefault, c->stream), "cudaMemcpy2DAsync");
+}
+template <typename T>
+static int copy_out(hank_ctx* c, T* dst_dense, const T* src_padded, size_t rows) {
+  return cuda_check(c, cudaMemcpy2DAsync(dst_dense, (size_t)c->n_a * sizeof(T), src_padded, (size_t)c->lda * sizeof(T),
+                                         (size_t)c->n_a * sizeof(T), rows, cudaMemcpyDefault, c->stream), "cudaMemcpy2DAsync");
+}
+
+// Tangent pass over the current tape for lanes given by dr/dw (already on device, [K][P]).
+static int tangent_pass(hank_ctx* c, int P, int K) {
+  RC(sw_backward_tangent(c, P, K, c->d_dr, c->d_dw, nullptr, c->d_dpol, nullptr));
+  int nw = 16;
+  RC(sw_forward_tangent(c, P, K, c->tape.pol, c->d_dpol, c->d_dkdpart, &nw));
+  k_reduce_partials<<<nblk((size_t)K * P), 256, 0, c->stream>>>(c->d_dkdpart, nw, K * P, c->d_dKD);
+  c->launches++;
+  return cuda_check(c, cudaGetLastError(), "k_reduce_partials");
+}
+
+}  // namespace hank
+
+using namespace hank;
+
+extern "C" {
+
+const char* hank_version(void) { return "hankb200 0.1 (sm_100a)"; }
+
+int hank_ctx_create(hank_ctx** out, int device, int n_a, int n_e, int T, const double* grid, const double* z,
+                    const double* Pi, double beta, double gamma, double borrow_cons) {
+  if (!out) return HANK_ERR_ARG;
+  *out = nullptr;
+  if (n_a < 2 || n_e < 1 || n_e > kMaxNE || T < 2 || !grid || !z || !Pi) return HANK_ERR_ARG;
+  hank_ctx* c = new hank_ctx;
+  *out = c;  // returned even on failure so hank_last_error() can be read; caller destroys it
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return set_error(c, HANK_ERR_CUDA, "no CUDA device available: libhankb200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return set_error(c, HANK_ERR_ARG, "bad device index");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  c->device = device;
+  c->smem_max = (int)prop.sharedMemPerBlockOptin;
+  c->sm_count = prop.multiProcessorCount;
+  c->n_a = n_a; c->n_e = n_e; c->T = T; c->P = T - 1; c->G = n_a * n_e; c->P_alloc = T - 1;
+  c->beta = beta; c->gamma = gamma; c->bc = borrow_cons;
+  c->h_grid.assign(grid, grid + n_a);
+  c->h_z.assign(z, z + n_e);
+  c->h_Pi.resize((size_t)n_e * n_e);
+  for (int e = 0; e < n_e; ++e)
+    for (int e2 = 0; e2 < n_e; ++e2) c->h_Pi[(size_t)e * n_e + e2] = Pi[e + (size_t)n_e * e2];
+  for (int a = 1; a < n_a; ++a)
+    if (!(grid[a] > grid[a - 1])) return set_error(c, HANK_ERR_ARG, "grid must be strictly increasing");
+  if (n_e != 3 && n_e != 7 && n_e != 11) return set_error(c, HANK_ERR_ARG, "n_e must be one of 3, 7, 11 in this build");
+  Shape s;
+  if (!pick_shape(n_a, &s)) return set_error(c, HANK_ERR_ARG, "n_a > 2048 is not supported in this build");
+  c->lda = s.NT * s.R; c->Gp = n_e * c->lda;
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&c->ev0));
+  CK(cudaEventCreate(&c->ev1));
+  const size_t PG = (size_t)c->P * c->Gp;
+  RC(dalloc(c, &c->d_grid, n_a));
+  CK(cudaMemcpy(c->d_grid, grid, n_a * sizeof(double), cudaMemcpyHostToDevice));
+  RC(dalloc(c, &c->d_valueT, c->Gp)); RC(dalloc(c, &c->d_D0, c->Gp));
+  CK(cudaMemset(c->d_valueT, 0, c->Gp * sizeof(double))); CK(cudaMemset(c->d_D0, 0, c->Gp * sizeof(double)));
+  RC(dalloc(c, &c->d_r, c->P)); RC(dalloc(c, &c->d_w, c->P));
+  Tape& tp = c->tape;
+  RC(dalloc(c, &tp.pol, PG)); RC(dalloc(c, &tp.bw, PG * BW_NF)); RC(dalloc(c, &tp.idx, PG));
+  RC(dalloc(c, &tp.rho, c->P)); RC(dalloc(c, &tp.fw, PG * FW_NF));
+  RC(dalloc(c, &tp.start, (size_t)c->P * n_e * (c->lda + 4))); RC(dalloc(c, &tp.mbr, PG));
+  RC(dalloc(c, &tp.value_first, c->Gp));
+  CK(cudaMemset(tp.pol, 0, PG * sizeof(double))); CK(cudaMemset(tp.bw, 0, PG * BW_NF * sizeof(double)));
+  CK(cudaMemset(tp.idx, 0, PG * sizeof(int))); CK(cudaMemset(tp.fw, 0, PG * FW_NF * sizeof(double)));
+  CK(cudaMemset(tp.start, 0, (size_t)c->P * n_e * (c->lda + 4) * sizeof(int)));
+  CK(cudaMemset(tp.mbr, 0, PG * sizeof(int))); CK(cudaMemset(tp.value_first, 0, c->Gp * sizeof(double)));
+  RC(dalloc(c, &c->d_kdpart, (size_t)c->P * 16)); RC(dalloc(c, &c->d_KD, c->P));
+  RC(dalloc(c, &c->d_status, 4));
+  CK(cudaMemset(c->d_status, 0, 4 * sizeof(int)));
+  CK(cudaMallocHost((void**)&c->h_status, 4 * sizeof(int)));
+  const size_t n = (size_t)4 * c->P;
+  RC(dalloc(c, &c->d_x, n)); RC(dalloc(c, &c->d_Z, c->P)); RC(dalloc(c, &c->d_F, n));
+  return HANK_OK;
+}
+
+void hank_ctx_destroy(hank_ctx* c) {
+  if (!c) return;
+  if (c->stream) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
+  hank_comm_destroy(c);
+  Tape& tp = c->tape;
+  dfree(c->d_grid); dfree(c->d_valueT); dfree(c->d_D0); dfree(c->d_r); dfree(c->d_w);
+  dfree(tp.pol); dfree(tp.bw); dfree(tp.idx); dfree(tp.rho); dfree(tp.fw); dfree(tp.start); dfree(tp.mbr);
+  dfree(tp.value_first);
+  dfree(c->d_dr); dfree(c->d_dw); dfree(c->d_dpol); dfree(c->d_dvalT); dfree(c->d_dvalue_first);
+  dfree(c->d_kdpart); dfree(c->d_KD); dfree(c->d_dkdpart); dfree(c->d_dKD); dfree(c->d_status);
+  dfree(c->d_x); dfree(c->d_Z); dfree(c->d_F); dfree(c->d_V); dfree(c->d_JV);
+  dfree(c->d_Jinv); dfree(c->d_newton); dfree(c->d_newton_i);
+  if (c->h_status) cudaFreeHost(c->h_status);
+  if (c->h_pin) cudaFreeHost(c->h_pin);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* hank_last_error(hank_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int hank_sync(hank_ctx* c) {
+  if (!c) return HANK_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  return check_status(c);
+}
+int hank_timer_start(hank_ctx* c) { CK(cudaEventRecord(c->ev0, c->stream)); return HANK_OK; }
+int hank_timer_stop(hank_ctx* c, float* ms) {
+  CK(cudaEventRecord(c->ev1, c->stream));
+  CK(cudaEventSynchronize(c->ev1));
+  CK(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+  return HANK_OK;
+}
+int64_t hank_launch_count(hank_ctx* c) { return c ? c->launches : 0; }
+int hank_reserve_lanes(hank_ctx* c, int K) {
+  CK(cudaSetDevice(c->device));
+  RC(ensure_lanes(c, K));
+  return HANK_OK;
+}
+
+int hank_set_terminal(hank_ctx* c, const double* v) {
+  CK(cudaSetDevice(c->device));
+  RC(copy_in(c, c->d_valueT, v, c->n_e));
+  CK(cudaStreamSynchronize(c->stream));
+  c->have_terminal = true; c->have_backward = false; c->linearized = false;
+  return HANK_OK;
+}
+int hank_set_initial_dist(hank_ctx* c, const double* D0) {
+  CK(cudaSetDevice(c->device));
+  RC(copy_in(c, c->d_D0, D0, c->n_e));
+  CK(cudaStreamSynchronize(c->stream));
+  c->have_D0 = true; c->have_forward = false; c->linearized = false;
+  return HANK_OK;
+}
+
+// ---- sweeps ------------------------------------------------------------------------------
+static int backward_dev(hank_ctx* c, const double* r, const double* w, int K, const double* dr, const double* dw) {
+  if (!c->have_terminal) return set_error(c, HANK_ERR_STATE, "hank_set_terminal has not been called");
+  if (K < 0 || (K > 0 && (!dr || !dw))) return set_error(c, HANK_ERR_ARG, "K > 0 needs dr and dw");
+  RC(sw_backward_primal(c, c->P, c->d_valueT, r, w));
+  c->have_backward = true; c->have_forward = false; c->K_last = 0;
+  if (K > 0) {
+    RC(ensure_lanes(c, K));
+    if (K > c->Kcap) return set_error(c, HANK_ERR_ARG, "K exceeds the lanes that fit in device memory; chunk the pass");
+    RC(sw_backward_tangent(c, c->P, K, dr, dw, nullptr, c->d_dpol, nullptr));
+    c->K_last = K;
+  }
+  return HANK_OK;
+}
+static int forward_dev(hank_ctx* c, const double* pol, int K, const double* dpol, double* KD, double* dKD) {
+  if (!c->have_D0) return set_error(c, HANK_ERR_STATE, "hank_set_initial_dist has not been called");
+  RC(sw_forward_primal(c, c->P, c->d_D0, pol, KD));
+  c->have_forward = true;
+  if (K > 0) {
+    int nw = 16;
+    RC(sw_forward_tangent(c, c->P, K, pol, dpol, c->d_dkdpart, &nw));
+    k_reduce_partials<<<nblk((size_t)K * c->P), 256, 0, c->stream>>>(c->d_dkdpart, nw, K * c->P, dKD);
+    c->launches++;
+    CK(cudaGetLastError());
+  }
+  return HANK_OK;
+}
+
+int hank_block_dev(hank_ctx* c, const double* r, const double* w, int K, const double* dr, const double* dw,
+                   double* KD, double* dKD) {
+  CK(cudaSetDevice(c->device));
+  RC(backward_dev(c, r, w, K, dr, dw));
+  return forward_dev(c, c->tape.pol, K, c->d_dpol, KD, dKD);
+}
+
+int hank_backward(hank_ctx* c, const double* r, const double* w, int K, const double* dr, const double* dw) {
+  CK(cudaSetDevice(c->device));
+  const int P = c->P;
+  if (K > 0) RC(ensure_lanes(c, K));
+  if (K > c->Kcap && K > 0) return set_error(c, HANK_ERR_ARG, "K exceeds the lanes that fit in device memory");
+  CK(cudaMemcpyAsync(c->d_r, r, P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_w, w, P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (K > 0) {
+    CK(cudaMemcpyAsync(c->d_dr, dr, (size_t)K * P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_dw, dw, (size_t)K * P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  }
+  RC(backward_dev(c, c->d_r, c->d_w, K, c->d_dr, c->d_dw));
+  c->linearized = false;
+  return check_status(c);
+}
+
+int hank_forward(hank_ctx* c, double* KD, double* dKD) {
+  CK(cudaSetDevice(c->device));
+  if (!c->have_backward) return set_error(c, HANK_ERR_STATE, "hank_forward needs a preceding hank_backward");
+  const int K = c->K_last, P = c->P;
+  RC(forward_dev(c, c->tape.pol, K, c->d_dpol, c->d_KD, c->d_dKD));
+  CK(cudaMemcpyAsync(KD, c->d_KD, P * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (K > 0 && dKD) CK(cudaMemcpyAsync(dKD, c->d_dKD, (size_t)K * P * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  return check_status(c);
+}
+
+int hank_forward_policies(hank_ctx* c, const double* policy, int K, const double* dpolicy, double* KD, double* dKD) {
+  CK(cudaSetDevice(c->device));
+  const int P = c->P;
+  if (K > 0) { RC(ensure_lanes(c, K)); if (K > c->Kcap) return set_error(c, HANK_ERR_ARG, "K exceeds device memory"); }
+  RC(copy_in(c, c->tape.pol, policy, (size_t)P * c->n_e));
+  if (K > 0) RC(copy_in(c, c->d_dpol, dpolicy, (size_t)K * P * c->n_e));
+  c->have_backward = false; c->linearized = false; c->K_last = K;
+  RC(forward_dev(c, c->tape.pol, K, c->d_dpol, c->d_KD, c->d_dKD));
+  CK(cudaMemcpyAsync(KD, c->d_KD, P * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (K > 0 && dKD) CK(cudaMemcpyAsync(dKD, c->d_dKD, (size_t)K * P * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  return check_status(c);
+}
+
+int hank_block(hank_ctx* c, const double* r, const double* w, int K, const double* dr, const double* dw,
+               double* KD, double* dKD) {
+  RC(hank_backward(c, r, w, K, dr, dw));
+  return hank_forward(c, KD, dKD);
+}
+
+int hank_egm_step(hank_ctx* c, const double* value_next, const double* dvalue_next, double r, double w, int K,
+                  const double* dr, const double* dw, double* value, double* policy, double* dvalue, double* dpolicy) {
+  CK(cudaSetDevice(c->device));
+  if (K < 0 || (K > 0 && (!dr || !dw))) return set_error(c, HANK_ERR_ARG, "K > 0 needs dr and dw");
+  if (K > 0) RC(ensure_lanes(c, K));
+  if (K > c->Kcap && K > 0) return set_error(c, HANK_ERR_ARG, "K exceeds device memory");
+  // scratch for the incoming value and its lanes
+  static thread_local int dummy = 0; (void)dummy;
+  dfree(c->d_dvalT); dfree(c->d_dvalue_first);
+  const int Gp = c->Gp;
+  RC(dalloc(c, &c->d_dvalT, (size_t)(K + 1) * Gp));
+  RC(dalloc(c, &c->d_dvalue_first, (size_t)std::max(K, 1) * Gp));
+  double* d_vn = c->d_dvalT + (size_t)K * Gp;
+  RC(copy_in(c, d_vn, value_next, c->n_e));
+  CK(cudaMemcpyAsync(c->d_r, &r, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_w, &w, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));  // r, w are stack temporaries
+  c->have_backward = false; c->have_forward = false; c->linearized = false; c->K_last = 0;
+  RC(sw_backward_primal(c, 1, d_vn, c->d_r, c->d_w));
+  if (K > 0) {
+    if (dvalue_next) RC(copy_in(c, c->d_dvalT, dvalue_next, (size_t)K * c->n_e));
+    CK(cudaMemcpyAsync(c->d_dr, dr, K * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_dw, dw, K * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    RC(sw_backward_tangent(c, 1, K, c->d_dr, c->d_dw, dvalue_next ? c->d_dvalT : nullptr, c->d_dpol, c->d_dvalue_first));
+  }
+  RC(copy_out(c, value, c->tape.value_first, c->n_e));
+  RC(copy_out(c, policy, c->tape.pol, c->n_e));
+  if (K > 0) {
+    RC(copy_out(c, dvalue, c->d_dvalue_first, (size_t)K * c->n_e));
+    RC(copy_out(c, dpolicy, c->d_dpol, (size_t)K * c->n_e));  // P = 1: lane stride is one padded grid
+  }
+  return check_status(c);
+}
+
+// ---- accessors ---------------------------------------------------------------------------
+int hank_get_policy(hank_ctx* c, int t, int lane, double* out) {
+  CK(cudaSetDevice(c->device));
+  if (t < 1 || t > c->P || lane < 0 || lane > c->K_last) return set_error(c, HANK_ERR_ARG, "t or lane out of range");
+  const double* src = lane == 0 ? c->tape.pol + (size_t)(t - 1) * c->Gp
+                                : c->d_dpol + ((size_t)(lane - 1) * c->P + (t - 1)) * c->Gp;
+  RC(copy_out(c, out, src, c->n_e));
+  CK(cudaStreamSynchronize(c->stream));
+  return HANK_OK;
+}
+int hank_get_dist(hank_ctx* c, int t, double* out) {
+  CK(cudaSetDevice(c->device));
+  if (!c->have_forward) return set_error(c, HANK_ERR_STATE, "no forward sweep has been run");
+  if (t < 1 || t > c->P) return set_error(c, HANK_ERR_ARG, "t out of range");
+  RC(copy_out(c, out, (const double*)(c->tape.fw + ((size_t)(t - 1) * FW_NF + FW_D) * c->Gp), c->n_e));
+  CK(cudaStreamSynchronize(c->stream));
+  return HANK_OK;
+}
+int hank_get_value_first(hank_ctx* c, int lane, double* out) {
+  CK(cudaSetDevice(c->device));
+  if (lane != 0) return set_error(c, HANK_ERR_ARG, "only the primal value is retained by the sweeps");
+  RC(copy_out(c, out, (const double*)c->tape.value_first, c->n_e));
+  CK(cudaStreamSynchronize(c->stream));
+  return HANK_OK;
+}
+int hank_get_brackets(hank_ctx* c, int t, int32_t* m) {
+  CK(cudaSetDevice(c->device));
+  if (!c->have_forward) return set_error(c, HANK_ERR_STATE, "no forward sweep has been run");
+  if (t < 1 || t > c->P) return set_error(c, HANK_ERR_ARG, "t out of range");
+  RC(copy_out(c, m, (const int32_t*)(c->tape.mbr + (size_t)(t - 1) * c->Gp), c->n_e));
+  CK(cudaStreamSynchronize(c->stream));
+  return HANK_OK;
+}
+int hank_lottery(hank_ctx* c, const double* policy, int32_t* m, double* omega) {
+  CK(cudaSetDevice(c->device));
+  const int G = c->G;
+  double* d_p = nullptr; int32_t* d_m = nullptr; double* d_o = nullptr;
+  RC(dalloc(c, &d_p, G)); RC(dalloc(c, &d_m, G)); RC(dalloc(c, &d_o, G));
+  CK(cudaMemcpyAsync(d_p, policy, G * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  k_lottery<<<nblk(G), 256, 0, c->stream>>>(c->d_grid, c->n_a, G, d_p, d_m, d_o);
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(m, d_m, G * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (omega) CK(cudaMemcpyAsync(omega, d_o, G * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  cudaFree(d_p); cudaFree(d_m); cudaFree(d_o);
+  return HANK_OK;
+}
+
+// ---- Krusell-Smith F and JVPs ---------------------------------------------------------------
+int hank_ks_configure(hank_ctx* c, double alpha, double delta, double ss_start_KS) {
+  c->alpha = alpha; c->delta = delta; c->ssKS = ss_start_KS; c->ks_ready = true; c->linearized = false;
+  return HANK_OK;
+}
+
+int hank_ks_linearize_dev(hank_ctx* c, const double* x, const double* Z, double* F) {
+  CK(cudaSetDevice(c->device));
+  if (!c->ks_ready) return set_error(c, HANK_ERR_STATE, "hank_ks_configure has not been called");
+  if (!c->have_terminal || !c->have_D0) return set_error(c, HANK_ERR_STATE, "terminal value / initial distribution not set");
+  const int P = c->P; const size_t n = (size_t)4 * P;
+  if (x != c->d_x) CK(cudaMemcpyAsync(c->d_x, x, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  if (Z != c->d_Z) CK(cudaMemcpyAsync(c->d_Z, Z, P * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  k_extract_rw<<<nblk(P), 256, 0, c->stream>>>(c->d_x, P, c->d_r, c->d_w);
+  c->launches++;
+  RC(backward_dev(c, c->d_r, c->d_w, 0, nullptr, nullptr));
+  RC(forward_dev(c, c->tape.pol, 0, nullptr, c->d_KD, nullptr));
+  k_ks_residual<<<nblk(P), 256, 0, c->stream>>>(P, c->alpha, c->delta, c->ssKS, c->d_x, c->d_KD, c->d_Z, F);
+  c->launches++;
+  CK(cudaGetLastError());
+  c->linearized = true;
+  return HANK_OK;
+}
+
+int hank_ks_jvp_dev(hank_ctx* c, int K, const double* V, double* JV) {
+  CK(cudaSetDevice(c->device));
+  if (!c->linearized) return set_error(c, HANK_ERR_STATE, "hank_ks_jvp needs a preceding hank_ks_linearize");
+  if (K < 1) return set_error(c, HANK_ERR_ARG, "K must be >= 1");
+  const int P = c->P; const size_t n = (size_t)4 * P;
+  RC(ensure_lanes(c, K));
+  for (int k0 = 0; k0 < K; k0 += c->Kcap) {
+    const int kc = std::min(c->Kcap, K - k0);
+    const double* Vc = V + (size_t)k0 * n;
+    k_extract_drdw<<<nblk((size_t)kc * P), 256, 0, c->stream>>>(Vc, P, kc, c->d_dr, c->d_dw);
+    c->launches++;
+    RC(tangent_pass(c, P, kc));
+    k_ks_residual_tangent<<<nblk((size_t)kc * P), 256, 0, c->stream>>>(P, kc, c->alpha, c->ssKS, c->d_x, c->d_Z, Vc,
+                                                                      c->d_dKD, JV + (size_t)k0 * n);
+    c->launches++;
+    CK(cudaGetLastError());
+  }
+  c->K_last = std::min(K, c->Kcap);
+  return HANK_OK;
+}
+
+int hank_ks_linearize(hank_ctx* c, const double* x, const double* Z, double* F) {
+  CK(cudaSetDevice(c->device));
+  const int P = c->P; const size_t n = (size_t)4 * P;
+  CK(cudaMemcpyAsync(c->d_x, x, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_Z, Z, P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  RC(hank_ks_linearize_dev(c, c->d_x, c->d_Z, c->d_F));
+  if (F) CK(cudaMemcpyAsync(F, c->d_F, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  int rc = check_status(c);
+  if (rc) c->linearized = false;
+  return rc;
+}
+
+int hank_ks_jvp(hank_ctx* c, int K, const double* V, double* JV) {
+  CK(cudaSetDevice(c->device));
+  if (K < 1) return set_error(c, HANK_ERR_ARG, "K must be >= 1");
+  const size_t n = (size_t)4 * c->P;
+  RC(ensure_V(c, K));
+  CK(cudaMemcpyAsync(c->d_V, V, n * K * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  RC(hank_ks_jvp_dev(c, K, c->d_V, c->d_JV));
+  CK(cudaMemcpyAsync(JV, c->d_JV, n * K * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  return check_status(c);
+}
+
+int hank_ks_jacobian_columns_dev(hank_ctx* c, int col_begin, int col_end, double* J) {
+  CK(cudaSetDevice(c->device));
+  if (!c->linearized) return set_error(c, HANK_ERR_STATE, "hank_ks_jacobian_columns needs a preceding hank_ks_linearize");
+  const int P = c->P, n = 4 * P;
+  if (col_begin < 1 || col_end > n + 1 || col_end <= col_begin) return set_error(c, HANK_ERR_ARG, "bad column range");
+  const int c0 = col_begin - 1, ncols = col_end - col_begin;
+  std::vector<int> lane_col, col_lane(ncols, -1);
+  for (int j = 0; j < ncols; ++j)
+    if (((c0 + j) & 3) >= 2) lane_col.push_back(c0 + j);
+  int Kh = (int)lane_col.size();
+  if (Kh > 0) RC(ensure_lanes(c, Kh));
+  int* d_lane_col = nullptr; int* d_col_lane = nullptr;
+  RC(dalloc(c, &d_lane_col, std::max(Kh, 1))); RC(dalloc(c, &d_col_lane, ncols));
+  const int chunk = Kh > 0 ? c->Kcap : 1;
+  // Y / KS columns first need no sweeps: handled by col_lane = -1. Household lanes go in chunks of
+  // Kcap; each chunk writes the columns it owns.
+  int done_cols = 0;  // columns [c0, c0+done_cols) written
+  for (int k0 = 0; k0 < std::max(Kh, 1); k0 += chunk) {
+    const int kc = Kh > 0 ? std::min(chunk, Kh - k0) : 0;
+    // column sub-range covered by this chunk: up to (not including) the first column of the next chunk
+    const int col_hi = (k0 + kc < Kh) ? lane_col[k0 + kc] - c0 : ncols;
+    const int col_lo = done_cols;
+    std::fill(col_lane.begin(), col_lane.end(), -1);
+    for (int l = 0; l < kc; ++l) col_lane[lane_col[k0 + l] - c0] = l;
+    if (kc > 0) {
+      CK(cudaMemcpyAsync(d_lane_col, lane_col.data() + k0, kc * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+      CK(cudaMemsetAsync(c->d_dr, 0, (size_t)kc * P * sizeof(double), c->stream));
+      CK(cudaMemsetAsync(c->d_dw, 0, (size_t)kc * P * sizeof(double), c->stream));
+      k_unit_seeds<<<nblk(kc), 256, 0, c->stream>>>(P, kc, d_lane_col, c->d_dr, c->d_dw);
+      c->launches++;
+      RC(tangent_pass(c, P, kc));
+    }
+    CK(cudaMemcpyAsync(d_col_lane, col_lane.data() + col_lo, (col_hi - col_lo) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    k_ks_jac_columns<<<nblk((size_t)(col_hi - col_lo) * P), 256, 0, c->stream>>>(
+        P, c0 + col_lo, col_hi - col_lo, c->alpha, c->ssKS, c->d_x, c->d_Z, d_col_lane, c->d_dKD, J + (size_t)col_lo * n);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));  // host vectors are reused by the next chunk
+    done_cols = col_hi;
+  }
+  cudaFree(d_lane_col); cudaFree(d_col_lane);
+  c->K_last = std::min(Kh, c->Kcap);
+  return HANK_OK;
+}
+
+int hank_ks_jacobian_columns(hank_ctx* c, int col_begin, int col_end, double* J) {
+  CK(cudaSetDevice(c->device));
+  const size_t n = (size_t)4 * c->P;
+  if (col_end <= col_begin) return set_error(c, HANK_ERR_ARG, "bad column range");
+  const int ncols = col_end - col_begin;
+  RC(ensure_V(c, ncols));
+  RC(hank_ks_jacobian_columns_dev(c, col_begin, col_end, c->d_JV));
+  CK(cudaMemcpyAsync(J, c->d_JV, n * ncols * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  return check_status(c);
+}
+
+}  // extern "C"

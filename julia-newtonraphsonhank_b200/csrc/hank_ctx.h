@@ -1,0 +1,81 @@
+// hank_ctx.h — the context object behind the C ABI (include/hankb200.h).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "hank_kernels.cuh"
+
+struct hank_ctx {
+  int device = 0;
+  int n_a = 0, n_e = 0, T = 0, P = 0, G = 0;
+  int lda = 0, Gp = 0;          // padded leading dimension NT*R >= n_a and n_e*lda
+  int P_alloc = 0;              // periods the tape / paths are allocated for
+  double beta = 0, gamma = 0, bc = 0;
+  std::vector<double> h_grid, h_z, h_Pi;  // h_Pi row-major [e][e2]
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int smem_max = 0, sm_count = 0;
+
+  double *d_grid = nullptr, *d_valueT = nullptr, *d_D0 = nullptr;
+  double *d_r = nullptr, *d_w = nullptr;
+  hank::Tape tape{};
+  bool have_terminal = false, have_D0 = false, have_backward = false, have_forward = false;
+
+  // tangent lanes
+  int Kcap = 0, K_last = 0;
+  double *d_dr = nullptr, *d_dw = nullptr, *d_dpol = nullptr;
+  double *d_dvalT = nullptr, *d_dvalue_first = nullptr;  // egm_step lanes
+  double *d_kdpart = nullptr, *d_KD = nullptr, *d_dkdpart = nullptr, *d_dKD = nullptr;
+  int* d_status = nullptr;
+  int* h_status = nullptr;  // pinned
+
+  // Krusell-Smith residual layer
+  bool ks_ready = false, linearized = false;
+  double alpha = 0, delta = 0, ssKS = 0;
+  double *d_x = nullptr, *d_Z = nullptr, *d_F = nullptr, *d_V = nullptr, *d_JV = nullptr;
+  int Vcap = 0;
+  double *h_pin = nullptr; size_t h_pin_bytes = 0;  // pinned staging for host-pointer calls
+
+  // dense solve (Newton)
+  void* solver = nullptr;  // cusolverDnHandle_t
+  double *d_Jinv = nullptr, *d_newton = nullptr;
+  int* d_newton_i = nullptr;
+
+  // NCCL
+  void* nccl_comm = nullptr;
+  int nranks = 1, rank = 0;
+
+  std::string err;
+  int64_t launches = 0;
+};
+
+namespace hank {
+
+struct Shape {  // launch configuration derived from (n_a, K, smem)
+  int NT, R;
+};
+inline bool pick_shape(int n_a, Shape* s) {
+  if (n_a <= 256) { *s = {256, 1}; return true; }
+  if (n_a <= 512) { *s = {512, 1}; return true; }
+  if (n_a <= 1024) { *s = {512, 2}; return true; }
+  if (n_a <= 2048) { *s = {512, 4}; return true; }
+  return false;
+}
+
+// Per-n_e launchers (explicitly instantiated in hank_ne*.cu). All return a hank_status.
+template <int NE>
+struct Sweeps {
+  static int backward_primal(hank_ctx* c, int P, const double* valueT, const double* r, const double* w);
+  static int backward_tangent(hank_ctx* c, int P, int K, const double* dr, const double* dw,
+                              const double* dvalT, double* dpol, double* dvalue_first);
+  static int forward_primal(hank_ctx* c, int P, const double* D0, const double* pol, double* KD);
+  static int forward_tangent(hank_ctx* c, int P, int K, const double* pol, const double* dpol,
+                             double* dkdpart, int* nw_out);
+  static int lanes_per_cta(hank_ctx* c, int K);
+};
+
+int set_error(hank_ctx* c, int code, const std::string& msg);
+int cuda_check(hank_ctx* c, cudaError_t e, const char* what);
+
+}  // namespace hank

@@ -1,0 +1,389 @@
+// hank_newton.cu — NewtonRaphsonHANK / y_Iteration (NewtonRaphson.jl:27-114) with every vector
+// resident on the device: the sweeps, the residuals, the preconditioner solve and the updates
+// run as kernels on the context's stream; the host only reads two norms per inner iteration to
+// evaluate the reference's stopping rules.
+//
+// Preconditioner solve J̅·R = F(x) − J(x)·y (NewtonRaphson.jl:97):
+//   solver 0: restarted GMRES(20), IterativeSolvers 0.9.4 defaults (restart = min(20,n),
+//             maxiter = n, reltol = sqrt(eps) of the call's initial residual, modified
+//             Gram-Schmidt), R reused as the initial guess — the reference's behaviour.  The
+//             second solve `gmres!(M, J̅, Λxy)` (:98) only feeds a printed quantity (:101, :108)
+//             and is skipped.
+//   solver 1: J̅⁻¹ formed once by cuSOLVER LU (getrf/getrs on the identity), then one FP64 GEMV
+//             per inner iteration.
+#include <cmath>
+#include <cstdio>
+#include <limits>
+#include <vector>
+#include <cusolverDn.h>
+#include "hank_ctx.h"
+#include "../../include/hankb200.h"
+
+namespace hank {
+
+#define CK(call)                                                   \
+  do {                                                             \
+    int rc__ = hank::cuda_check(c, (call), #call);                 \
+    if (rc__) return rc__;                                         \
+  } while (0)
+#define RC(call)                 \
+  do {                           \
+    int rc__ = (call);           \
+    if (rc__) return rc__;       \
+  } while (0)
+
+constexpr int kSplit = 16;   // column splits of the GEMV
+constexpr int kRestartMax = 20;
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  // blockDim.x multiple of 32, <= 1024
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (w == 0) {
+    s = l < nw ? red[l] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (l == 0) red[32] = s;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+// part[s][i] = Σ_{j in split s} A[i + j n] v[j]   (A column-major)
+__global__ void k_gemv_partial(const double* __restrict__ A, const double* __restrict__ v, int n, double* part) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = blockIdx.y;
+  const int cs = (n + kSplit - 1) / kSplit;
+  const int j0 = s * cs, j1 = min(n, j0 + cs);
+  if (i >= n) return;
+  double acc = 0.0;
+  for (int j = j0; j < j1; ++j) acc = fma(A[(size_t)j * n + i], __ldg(v + j), acc);
+  part[(size_t)s * n + i] = acc;
+}
+__global__ void k_sub(const double* a, const double* b, int n, double* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] - b[i];
+}
+__global__ void k_fill(double* a, int n, double v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = v;
+}
+__global__ void k_identity(double* A, int n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (size_t)n * n) A[i] = (i / n == i % n) ? 1.0 : 0.0;
+}
+// scal[0] = ||a - b||, scal[1] = ||a||   (single block)
+__global__ void k_norms(const double* a, const double* b, int n, double* scal) {
+  __shared__ double red[33];
+  double d = 0.0, s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { double t = a[i] - b[i]; d += t * t; s += a[i] * a[i]; }
+  d = block_sum(d, red);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) { scal[0] = sqrt(d); scal[1] = sqrt(s); }
+}
+// LU mode: R = Σ_s part; y_old = y; y = y_old + α R; norms (single block)
+__global__ void k_update_from_partial(const double* __restrict__ part, int n, double alpha, double* R, double* y,
+                                      double* yold, double* scal) {
+  __shared__ double red[33];
+  double d = 0.0, s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double r = 0.0;
+    for (int k = 0; k < kSplit; ++k) r += part[(size_t)k * n + i];
+    R[i] = r;
+    const double yo = y[i], yn = yo + alpha * r;
+    yold[i] = yo; y[i] = yn;
+    const double t = yn - yo;
+    d += t * t; s += yn * yn;
+  }
+  d = block_sum(d, red);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) { scal[0] = sqrt(d); scal[1] = sqrt(s); }
+}
+__global__ void k_update_y(const double* __restrict__ R, int n, double alpha, double* y, double* yold, double* scal) {
+  __shared__ double red[33];
+  double d = 0.0, s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double yo = y[i], yn = yo + alpha * R[i];
+    yold[i] = yo; y[i] = yn;
+    const double t = yn - yo;
+    d += t * t; s += yn * yn;
+  }
+  d = block_sum(d, red);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) { scal[0] = sqrt(d); scal[1] = sqrt(s); }
+}
+__global__ void k_xmy(double* x, const double* y, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] -= y[i];
+}
+
+// ---- GMRES pieces (single block each; n ~ 10^3) -------------------------------------------
+// gs: [0]=beta(residual.β) [1]=accumulator [2]=current [3]=beta of the cycle (init! return)
+// V[:,0] = (b − Σ part) / β
+__global__ void k_gmres_init(const double* __restrict__ part, const double* __restrict__ b, int n, double* V,
+                             double* gs, double* nullvec) {
+  __shared__ double red[33];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double ax = 0.0;
+    for (int k = 0; k < kSplit; ++k) ax += part[(size_t)k * n + i];
+    const double v = b[i] - ax;
+    V[i] = v; s += v * v;
+  }
+  s = block_sum(s, red);
+  const double beta = sqrt(s), ib = 1.0 / beta;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) V[i] *= ib;
+  if (threadIdx.x == 0) { gs[0] = beta; gs[1] = 1.0; gs[2] = beta; gs[3] = beta; nullvec[0] = 1.0; }
+}
+// Arnoldi step k (1-based): w = Σ part = A V[:,k-1]; MGS against V[:,0..k-1]; H[:,k-1]; residual update
+__global__ void k_gmres_step(const double* __restrict__ part, int n, int k, double* V, double* H, double* gs,
+                             double* nullvec) {
+  __shared__ double red[33];
+  double* w = V + (size_t)k * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double a = 0.0;
+    for (int s = 0; s < kSplit; ++s) a += part[(size_t)s * n + i];
+    w[i] = a;
+  }
+  __syncthreads();
+  const int ld = kRestartMax + 1;
+  for (int c = 0; c < k; ++c) {
+    const double* vc = V + (size_t)c * n;
+    double h = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) h += vc[i] * w[i];
+    h = block_sum(h, red);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) w[i] -= h * vc[i];
+    if (threadIdx.x == 0) H[(size_t)(k - 1) * ld + c] = h;
+    __syncthreads();
+  }
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += w[i] * w[i];
+  s = block_sum(s, red);
+  const double nr = sqrt(s), inr = 1.0 / nr;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) w[i] *= inr;
+  if (threadIdx.x == 0) {
+    H[(size_t)(k - 1) * ld + k] = nr;
+    double d = 0.0;
+    for (int c = 0; c < k; ++c) d += nullvec[c] * H[(size_t)(k - 1) * ld + c];
+    const double nv = -(d / nr);
+    nullvec[k] = nv;
+    gs[1] += nv * nv;
+    gs[2] = gs[0] / sqrt(gs[1]);
+  }
+}
+// Least squares on H[0:kk, 0:kk-1] by Givens rotations, x += V[:,0:kk-1] y
+__global__ void k_gmres_update(int n, int kk, const double* __restrict__ V, const double* __restrict__ H,
+                               const double* __restrict__ gs, double* x) {
+  __shared__ double Hc[(kRestartMax + 1) * kRestartMax];
+  __shared__ double rhs[kRestartMax + 1];
+  const int ld = kRestartMax + 1, wd = kk - 1;
+  for (int i = threadIdx.x; i < ld * kRestartMax; i += blockDim.x) Hc[i] = H[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i <= wd; ++i) rhs[i] = 0.0;
+    rhs[0] = gs[3];
+    for (int i = 0; i < wd; ++i) {
+      const double a = Hc[i * ld + i], b = Hc[i * ld + i + 1];
+      const double rr = hypot(a, b), cs = a / rr, sn = b / rr;
+      Hc[i * ld + i] = rr; Hc[i * ld + i + 1] = 0.0;
+      for (int j = i + 1; j < wd; ++j) {
+        const double t1 = Hc[j * ld + i], t2 = Hc[j * ld + i + 1];
+        Hc[j * ld + i] = cs * t1 + sn * t2;
+        Hc[j * ld + i + 1] = -sn * t1 + cs * t2;
+      }
+      const double t1 = rhs[i], t2 = rhs[i + 1];
+      rhs[i] = cs * t1 + sn * t2; rhs[i + 1] = -sn * t1 + cs * t2;
+    }
+    for (int i = wd - 1; i >= 0; --i) {
+      double s = rhs[i];
+      for (int j = i + 1; j < wd; ++j) s -= Hc[j * ld + i] * rhs[j];
+      rhs[i] = s / Hc[i * ld + i];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double a = x[i];
+    for (int j = 0; j < wd; ++j) a += V[(size_t)j * n + i] * rhs[j];
+    x[i] = a;
+  }
+}
+
+struct NewtonBufs {
+  double *x, *y, *yold, *Fx, *Lxy, *rhs, *R, *part, *scal, *Vb, *H, *gs, *nullvec, *J;
+};
+
+static int gemv_partial(hank_ctx* c, const double* A, const double* v, int n, double* part) {
+  dim3 grid((n + 127) / 128, kSplit);
+  k_gemv_partial<<<grid, 128, 0, c->stream>>>(A, v, n, part);
+  c->launches++;
+  return cuda_check(c, cudaGetLastError(), "k_gemv_partial");
+}
+
+// gmres!(x, A, b) on the device; returns inner iterations through *iters.
+static int device_gmres(hank_ctx* c, const NewtonBufs& B, int n, double* x, const double* b, double* h_scal, long* iters) {
+  const int restart = std::min(kRestartMax, n), maxiter = n;
+  const double reltol = std::sqrt(std::numeric_limits<double>::epsilon());
+  auto read_gs = [&](double* out) -> int {
+    CK(cudaMemcpyAsync(out, B.gs, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+  };
+  RC(gemv_partial(c, B.J, x, n, B.part));
+  k_gmres_init<<<1, 1024, 0, c->stream>>>(B.part, b, n, B.Vb, B.gs, B.nullvec);
+  c->launches++;
+  RC(read_gs(h_scal));
+  double current = h_scal[2];
+  const double tol = std::max(reltol * current, 0.0);
+  int k = 1, iteration = 0;
+  while (true) {
+    if (iteration >= maxiter || current <= tol) {
+      if (k > 1) { k_gmres_update<<<1, 1024, 0, c->stream>>>(n, k, B.Vb, B.H, B.gs, x); c->launches++; }
+      break;
+    }
+    RC(gemv_partial(c, B.J, B.Vb + (size_t)(k - 1) * n, n, B.part));
+    k_gmres_step<<<1, 1024, 0, c->stream>>>(B.part, n, k, B.Vb, B.H, B.gs, B.nullvec);
+    c->launches++;
+    RC(read_gs(h_scal));
+    current = h_scal[2];
+    ++k;
+    if (k == restart + 1) {
+      k_gmres_update<<<1, 1024, 0, c->stream>>>(n, k, B.Vb, B.H, B.gs, x);
+      c->launches++;
+      k = 1;
+      if (!(iteration >= maxiter || current <= tol)) {
+        RC(gemv_partial(c, B.J, x, n, B.part));
+        CK(cudaMemsetAsync(B.H, 0, sizeof(double) * (kRestartMax + 1) * kRestartMax, c->stream));
+        k_gmres_init<<<1, 1024, 0, c->stream>>>(B.part, b, n, B.Vb, B.gs, B.nullvec);
+        c->launches++;
+      }
+    }
+    ++iteration;
+  }
+  *iters += iteration;
+  return cuda_check(c, cudaGetLastError(), "gmres");
+}
+
+static int status_now(hank_ctx* c) {
+  CK(cudaMemcpyAsync(c->h_status, c->d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->h_status[0] == 0) return 0;
+  return hank_sync(c);  // formats the message and clears the flag
+}
+
+}  // namespace hank
+
+using namespace hank;
+
+extern "C" int hank_newton_solve(hank_ctx* c, const double* Jbar, const double* x0, const double* Z, double eps,
+                                 double eps_inner, int solver, double* x_out, double* stats, int* inner_counts) {
+  if (!c || !Jbar || !x0 || !Z || !x_out) return HANK_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  if (!c->ks_ready) return set_error(c, HANK_ERR_STATE, "hank_ks_configure has not been called");
+  if (solver != 0 && solver != 1) return set_error(c, HANK_ERR_ARG, "solver must be 0 (gmres) or 1 (lu)");
+  const int P = c->P, n = 4 * P;
+  const size_t nn = (size_t)n * n;
+  // workspace
+  const size_t nvec = 7, extra = (size_t)kSplit * n + 16 + (size_t)(kRestartMax + 1) * n +
+                                 (size_t)(kRestartMax + 1) * kRestartMax + 8 + (kRestartMax + 1);
+  if (c->d_newton) { cudaFree(c->d_newton); c->d_newton = nullptr; }
+  if (c->d_Jinv) { cudaFree(c->d_Jinv); c->d_Jinv = nullptr; }
+  CK(cudaMalloc((void**)&c->d_newton, (nvec * n + extra) * sizeof(double)));
+  CK(cudaMalloc((void**)&c->d_Jinv, nn * sizeof(double) * (solver == 1 ? 2 : 1)));
+  NewtonBufs B;
+  double* p = c->d_newton;
+  B.x = p; p += n; B.y = p; p += n; B.yold = p; p += n; B.Fx = p; p += n; B.Lxy = p; p += n; B.rhs = p; p += n;
+  B.R = p; p += n; B.part = p; p += (size_t)kSplit * n; B.scal = p; p += 16;
+  B.Vb = p; p += (size_t)(kRestartMax + 1) * n; B.H = p; p += (size_t)(kRestartMax + 1) * kRestartMax;
+  B.gs = p; p += 8; B.nullvec = p;
+  B.J = c->d_Jinv;
+  CK(cudaMemcpyAsync(B.J, Jbar, nn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(B.x, x0, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(B.y, x0, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_Z, Z, P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemsetAsync(B.H, 0, sizeof(double) * (kRestartMax + 1) * kRestartMax, c->stream));
+  if (solver == 1) {
+    // J̅⁻¹ once: LU (cuSOLVER getrf) then getrs on the identity
+    cusolverDnHandle_t h = (cusolverDnHandle_t)c->solver;
+    if (!h) {
+      if (cusolverDnCreate(&h) != CUSOLVER_STATUS_SUCCESS) return set_error(c, HANK_ERR_CUDA, "cusolverDnCreate failed");
+      c->solver = h;
+    }
+    cusolverDnSetStream(h, c->stream);
+    double* LU = c->d_Jinv + nn;  // second half holds the factors, first half becomes the inverse
+    CK(cudaMemcpyAsync(LU, B.J, nn * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    int lwork = 0;
+    if (cusolverDnDgetrf_bufferSize(h, n, n, LU, n, &lwork) != CUSOLVER_STATUS_SUCCESS)
+      return set_error(c, HANK_ERR_CUDA, "cusolverDnDgetrf_bufferSize failed");
+    double* work = nullptr; int* ipiv = nullptr;
+    CK(cudaMalloc((void**)&work, sizeof(double) * std::max(lwork, 1)));
+    CK(cudaMalloc((void**)&ipiv, sizeof(int) * (n + 1)));
+    int* info = ipiv + n;
+    cusolverStatus_t s1 = cusolverDnDgetrf(h, n, n, LU, n, work, ipiv, info);
+    k_identity<<<(unsigned)((nn + 255) / 256), 256, 0, c->stream>>>(B.J, n);
+    c->launches += 2;
+    cusolverStatus_t s2 = cusolverDnDgetrs(h, CUBLAS_OP_N, n, n, LU, n, ipiv, B.J, n, info);
+    int h_info = 0;
+    CK(cudaMemcpyAsync(&h_info, info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(work); cudaFree(ipiv);
+    if (s1 != CUSOLVER_STATUS_SUCCESS || s2 != CUSOLVER_STATUS_SUCCESS || h_info != 0)
+      return set_error(c, HANK_ERR_CUDA, "LU factorisation of Jbar failed (singular or cuSOLVER error)");
+  }
+  double h_scal[4] = {0, 0, 0, 0};
+  auto read_scal = [&]() -> int {
+    CK(cudaMemcpyAsync(h_scal, B.scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_status, c->d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->h_status[0] != 0) return hank_sync(c);
+    return 0;
+  };
+  const int nb = (n + 255) / 256;
+  int outer = 1; long jvps = 0, fevals = 0, gm = 0;
+  // ||y|| for the first outer test (y = x0)
+  k_norms<<<1, 1024, 0, c->stream>>>(B.y, B.y, n, B.scal);
+  c->launches++;
+  RC(read_scal());
+  double ynorm = h_scal[1];
+  while (eps < ynorm && outer < 100) {
+    RC(hank_ks_linearize_dev(c, B.x, c->d_Z, B.Fx));
+    ++fevals;
+    k_fill<<<nb, 256, 0, c->stream>>>(B.yold, n, 1.0);
+    k_fill<<<nb, 256, 0, c->stream>>>(B.R, n, 1.0);
+    k_norms<<<1, 1024, 0, c->stream>>>(B.y, B.yold, n, B.scal);
+    c->launches += 3;
+    RC(read_scal());
+    double diff = h_scal[0];
+    int inner = 0;
+    while (eps_inner < diff) {
+      RC(hank_ks_jvp_dev(c, 1, B.y, B.Lxy));
+      ++jvps; ++inner;
+      k_sub<<<nb, 256, 0, c->stream>>>(B.Fx, B.Lxy, n, B.rhs);
+      c->launches++;
+      if (solver == 1) {
+        RC(gemv_partial(c, B.J, B.rhs, n, B.part));
+        k_update_from_partial<<<1, 1024, 0, c->stream>>>(B.part, n, 0.5, B.R, B.y, B.yold, B.scal);
+        c->launches++;
+      } else {
+        RC(status_now(c));
+        RC(device_gmres(c, B, n, B.R, B.rhs, h_scal, &gm));
+        k_update_y<<<1, 1024, 0, c->stream>>>(B.R, n, 0.5, B.y, B.yold, B.scal);
+        c->launches++;
+      }
+      RC(read_scal());
+      diff = h_scal[0]; ynorm = h_scal[1];
+      if (!std::isfinite(diff)) return set_error(c, HANK_ERR_NOCONV, "Newton inner iteration diverged (non-finite step)");
+    }
+    if (inner_counts && outer - 1 < 100) inner_counts[outer - 1] = inner;
+    k_xmy<<<nb, 256, 0, c->stream>>>(B.x, B.y, n);
+    c->launches++;
+    ++outer;
+  }
+  CK(cudaMemcpyAsync(x_out, B.x, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (stats) { stats[0] = outer - 1; stats[1] = (double)jvps; stats[2] = (double)fevals; stats[3] = ynorm; stats[4] = (double)gm; }
+  if (eps < ynorm) return set_error(c, HANK_ERR_NOCONV, "Newton outer iteration cap (100) reached");
+  return HANK_OK;
+}

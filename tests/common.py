@@ -1,0 +1,49 @@
+"""Shared deterministic inputs for the tests.  Test infrastructure: uses the oracle."""
+import numpy as np
+
+from oracle import oracle as O
+
+KS = dict(beta=0.98, gamma=2.0, borrow_cons=0.0, alpha=0.36, delta=0.08, rho=0.966, sigma=0.283)
+
+# parity tolerance of the north star: 1e-10 relative / 1e-12 absolute in FP64
+RTOL, ATOL = 1e-10, 1e-12
+
+
+def close(a, b, rtol=RTOL, atol=ATOL):
+    a = np.asarray(a); b = np.asarray(b)
+    return bool(np.all(np.abs(a - b) <= atol + rtol * np.abs(b)))
+
+
+def maxerr(a, b):
+    a = np.asarray(a); b = np.asarray(b)
+    return float(np.max(np.abs(a - b) / (ATOL / RTOL + np.abs(b))))  # in units of rtol-equivalent
+
+
+def model_inputs(n_a, n_e, gamma=2.0, borrow_cons=0.0, amax=200.0):
+    grid = O.double_exponential(n_a, 0.0, amax)
+    z, Pi, _ = O.rouwenhorst(n_e, KS["rho"], KS["sigma"])
+    return dict(grid=grid, z=z, Pi=Pi, beta=KS["beta"], gamma=gamma, borrow_cons=borrow_cons)
+
+
+def synthetic(n_a, n_e, T, K=0, gamma=2.0, seed=1234, rbar=0.015, wbar=1.35, c0=0.1):
+    """Synthetic-throughput regime (ii): closed-form monotone terminal value, uniform D0,
+    smooth r/w paths, N(0,1) tangent seeds."""
+    m = model_inputs(n_a, n_e, gamma)
+    P = T - 1
+    g, z = m["grid"], m["z"]
+    vT = (1 + rbar) * ((rbar * g[None, :] + wbar * z[:, None]) + c0) ** (-gamma)
+    D0 = np.full((n_e, n_a), 1.0 / (n_a * n_e))
+    t = np.arange(1, P + 1)
+    r = rbar * (1 + 0.1 * 0.9 ** t); w = wbar * (1 + 0.05 * 0.9 ** t)
+    rng = np.random.default_rng(seed)
+    dr = rng.standard_normal((K, P)); dw = rng.standard_normal((K, P))
+    return dict(m=m, T=T, P=P, vT=vT, D0=D0, r=r, w=w, dr=dr, dw=dw)
+
+
+def make_oracle(m, T):
+    return O.Oracle(m["grid"], m["z"], m["Pi"], m["beta"], m["gamma"], m["borrow_cons"], T)
+
+
+def make_block(m, T, device=0):
+    from hankb200.household import HouseholdBlock
+    return HouseholdBlock(m["grid"], m["z"], m["Pi"], m["beta"], m["gamma"], m["borrow_cons"], T, device=device)
