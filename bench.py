@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hankb200 household block.
+
+Workload (BASELINE.json configs[1]/[2]): Krusell-Smith, T=300 (P=299), 500 assets x 7 income
+states, model-consistent inputs (steady-state record from tests/golden/ss_500x7_T300.npz, shock
+Z_t = 1 + 0.8^t, RunMain.jl:50-51).  One STEP = one pass of the hot path over one batch:
+linearise F at x (primal EGM backward sweep + primal lottery forward sweep + residuals), then K
+dense JVP directions as batched tangent lanes (backward tangent sweep, forward tangent sweep,
+aggregation, residual tangents).  metric = JVPs per second (direction x full sweep pair).
+With --gpus N (one process per GPU, torchrun) every rank carries K lanes (weak scaling) and the
+n x K column blocks are all-gathered with NCCL (hank_allgather_columns_dev).
+
+Prints ONE JSON line (rank 0).  `value` has inputs resident in HBM; `e2e` goes through the
+host-pointer C ABI (hank_ks_linearize + hank_ks_jvp) with pinned host buffers, copies inside the
+timed region.  `--impl reference` times the CPU oracle (single-thread C++ restatement of the
+reference's Julia path; Julia is not installed in this image) on a bounded sample.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "julia-newtonraphsonhank_b200"))
+
+WORKLOADS = {
+    "ks_500x7_T300": dict(fixture="ss_500x7_T300.npz", desc="Krusell-Smith T=300, 500 assets x 7 income states"),
+    "ks_1000x7_T300": dict(fixture="ss_1000x7_T300.npz", desc="Krusell-Smith T=300, 1000 assets x 7 income states"),
+}
+METRIC, UNIT = "jvps_per_sec", "JVP/s"
+
+
+def load_fixture(name):
+    g = np.load(os.path.join(ROOT, "tests", "golden", WORKLOADS[name]["fixture"]))
+    T = int(g["T"]); P = T - 1
+    vars_ = g["ss_vars"]
+    return dict(g=g, T=T, P=P, n=4 * P, n_a=int(g["n_a"]), n_e=int(g["n_e"]),
+                x0=np.tile(vars_[:4], P), Z=1.0 + 0.8 ** np.arange(1, P + 1),
+                ks=(float(g["alpha"]), float(g["delta"]), float(vars_[1])))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args):
+    """CPU arm: the oracle (kind "port") on the same workload, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.build()
+    fx = load_fixture(args.workload)
+    g = fx["g"]
+    orc = O.Oracle(g["grid"], g["z"], g["Pi"], float(g["beta"]), float(g["gamma"]), float(g["borrow_cons"]), fx["T"])
+    Kc = args.cpu_lanes
+    rng = np.random.default_rng(1234)
+    V = rng.standard_normal((Kc, fx["n"]))
+    def step():
+        orc.ks_fjvp(fx["ks"], g["ss_value"], g["ss_D"], fx["Z"], fx["x0"], V)
+    for _ in range(min(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = Kc * args.steps / dt
+    cores = 1
+    sample = f"{Kc} of the GPU arm's {args.lanes} lanes per step (primal + {Kc} tangent lanes), {args.steps} steps"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": WORKLOADS[args.workload]["desc"], "lanes_per_step": Kc},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "note": "single-thread C++ restatement of the reference CPU path; Julia is not installed "
+                                 "and the reference has no threading (host nproc=%d)" % os.cpu_count()},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="hankb200", choices=["hankb200", "reference"])
+    ap.add_argument("--workload", default="ks_500x7_T300", choices=sorted(WORKLOADS))
+    ap.add_argument("--lanes", type=int, default=592, help="tangent lanes per GPU per step (4 per SM x 148 SMs)")
+    ap.add_argument("--cpu-lanes", type=int, default=32, help="lanes per step of the CPU sample")
+    ap.add_argument("--no-newton", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from hankb200 import HouseholdBlock
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: hankb200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    fx = load_fixture(args.workload)
+    g = fx["g"]; P, n, K = fx["P"], fx["n"], args.lanes
+    blk = HouseholdBlock(g["grid"], g["z"], g["Pi"], float(g["beta"]), float(g["gamma"]), float(g["borrow_cons"]),
+                         fx["T"], device=local)
+    L = blk._L; h = blk.handle
+    blk.set_terminal(g["ss_value"]); blk.set_initial_dist(g["ss_D"])
+    blk.ks_configure(*fx["ks"])
+    blk.reserve_lanes(K)
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt = torch.tensor(list(HouseholdBlock.comm_unique_id()), dtype=torch.uint8, device=dev)
+        dist.broadcast(idt, 0)
+        blk.comm_init(world, rank, bytes(idt.cpu().numpy().tolist()))
+
+    # ---- device-resident inputs (value) and pinned host inputs (e2e) ----------------------------
+    rng = np.random.default_rng(1234 + rank)
+    Vh = torch.from_numpy(rng.standard_normal((K, n))).pin_memory()
+    xh = torch.from_numpy(fx["x0"].copy()).pin_memory(); Zh = torch.from_numpy(fx["Z"].copy()).pin_memory()
+    Fh = torch.empty(n, dtype=torch.float64).pin_memory(); JVh = torch.empty((K, n), dtype=torch.float64).pin_memory()
+    Vd = Vh.to(dev); xd = xh.to(dev); Zd = Zh.to(dev)
+    Fd = torch.empty(n, dtype=torch.float64, device=dev); JVd = torch.empty((K, n), dtype=torch.float64, device=dev)
+    ALLd = torch.empty((world * K, n), dtype=torch.float64, device=dev) if world > 1 else None
+    torch.cuda.synchronize()
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    dp = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_double))
+
+    def step_dev():
+        blk._ck(L.hank_ks_linearize_dev(h, vp(xd), vp(Zd), vp(Fd)))
+        blk._ck(L.hank_ks_jvp_dev(h, K, vp(Vd), vp(JVd)))
+        if world > 1:
+            blk._ck(L.hank_allgather_columns_dev(h, vp(JVd), K * n, vp(ALLd)))
+
+    def step_e2e():
+        blk._ck(L.hank_ks_linearize(h, dp(xh), dp(Zh), dp(Fh)))
+        blk._ck(L.hank_ks_jvp(h, K, dp(Vh), dp(JVh)))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        blk.sync()
+
+    def timed(fn, steps):
+        barrier()
+        t0 = time.time()
+        blk.timer_start()
+        for _ in range(steps):
+            fn()
+        ms = blk.timer_stop()
+        blk.sync()
+        t1 = time.time()
+        barrier()
+        if world > 1:
+            tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms, t0, t1
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    blk.sync()
+    blk.profile(True); blk.kernel_times(reset=True)
+    lc0 = blk.launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, t0, t1 = timed(step_dev, args.steps)
+    clocks = sampler.stop(t0, t1) if sampler else None
+    launches = blk.launch_count() - lc0
+    kt = blk.kernel_times(reset=True)
+    blk.profile(False)
+    value = world * K * args.steps / (ms * 1e-3)
+
+    # ---- e2e through the host-pointer C ABI ------------------------------------------------------
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+    e2e_val = world * K * args.steps / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (algorithmic bytes: 8*G*P*K per tangent sweep) ----------
+    G = fx["n_a"] * fx["n_e"]
+    peak, peak_src = peaks()
+    alg = 8.0 * G * P * K
+    per = {k: (v[0] / v[1] if v[1] else None) for k, v in kt.items()}
+    dom = max(("backward_tangent", "forward_tangent"), key=lambda k: per[k] or 0.0)
+    ach = alg / (per[dom] * 1e-3) / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get(args.workload, {}).get(dom)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                "kernel_ms_per_launch": per,
+                "sweep_pair_GBps": 2 * alg / ((per["backward_tangent"] + per["forward_tangent"]) * 1e-3) / 1e9}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": WORKLOADS[args.workload]["desc"], "lanes_per_gpu_per_step": K,
+                   "step": "linearise F(x) (primal sweeps) + K-lane JVP (tangent sweeps) + residual tangents"
+                           + (" + NCCL all-gather of n x K columns" if world > 1 else ""),
+                   "l2": "inputs larger than L2 (policy-tangent stream %.2f GB per step vs 126 MB L2)" % (alg / 1e9)},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(8 * (n * K + n + P)),
+                "d2h_bytes_per_step": int(8 * (n * K + n)), "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+    }
+
+    # ---- extras at N = 1: Jacobian build, Newton solve, CPU baseline ------------------------------
+    if world == 1 and not args.no_newton:
+        ones = np.ones(P)
+        blk.linearize(fx["x0"], ones)
+        blk.sync(); blk.timer_start()
+        Jd = torch.empty((n, n), dtype=torch.float64, device=dev)
+        blk._ck(L.hank_ks_jacobian_columns_dev(h, 1, n + 1, vp(Jd)))
+        jac_ms = blk.timer_stop()
+        Jbar = Jd.cpu().numpy().T.copy()   # device buffer is column-major
+        tw = time.perf_counter()
+        x, st = blk.newton_solve(Jbar, fx["x0"], fx["Z"], solver="lu")
+        newton_ms = 1e3 * (time.perf_counter() - tw)
+        tw = time.perf_counter()
+        x, st = blk.newton_solve(Jbar, fx["x0"], fx["Z"], solver="lu")
+        newton_ms = min(newton_ms, 1e3 * (time.perf_counter() - tw))
+        Fx = blk.linearize(x, fx["Z"])
+        out["jacobian_build"] = {"ms": jac_ms, "columns": n, "household_lanes": n // 2,
+                                 "note": "full n x n sequence-space Jacobian by unit-seed lanes; Y/KS columns skip the sweeps"}
+        out["newton"] = {"ms_per_solve": newton_ms, "solver": "lu", "outer": st["outer"], "jvps": st["jvps"],
+                         "inner": st["inner"], "jvps_per_sec_k1": st["jvps"] / (newton_ms * 1e-3),
+                         "residual_norm": float(np.linalg.norm(Fx)), "timing": "host wall clock around hank_newton_solve (min of 2)"}
+    if world == 1 and not args.no_cpu:
+        from oracle import oracle as O
+        O.build()
+        orc = O.Oracle(g["grid"], g["z"], g["Pi"], float(g["beta"]), float(g["gamma"]), float(g["borrow_cons"]), fx["T"])
+        Kc = args.cpu_lanes
+        Vc = Vh.numpy()[:Kc]
+        orc.ks_fjvp(fx["ks"], g["ss_value"], g["ss_D"], fx["Z"], fx["x0"])  # warm-up (primal only)
+        tw = time.perf_counter()
+        Fc, JVc = orc.ks_fjvp(fx["ks"], g["ss_value"], g["ss_D"], fx["Z"], fx["x0"], Vc)
+        dtc = time.perf_counter() - tw
+        # the CPU sample doubles as an in-run parity check of the GPU result
+        err = float(np.max(np.abs(JVh.numpy()[:Kc] - JVc) / (1e-12 * max(1.0, np.abs(JVc).max()) + 1e-10 * np.abs(JVc))))
+        out["cpu_baseline"] = {"value": Kc / dtc, "unit": UNIT, "cores": 1, "kind": "port",
+                               "sample": f"1 step of primal + {Kc} of the {K} lanes ({dtc:.1f} s)",
+                               "host_nproc": os.cpu_count(), "parity_max_err_over_tol": err,
+                               "note": "single-thread C++ restatement (oracle/); Julia is not installed in this image"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -61,6 +61,12 @@ int hank_timer_start(hank_ctx* ctx);
 int hank_timer_stop(hank_ctx* ctx, float* ms);
 /* Kernels launched by this ctx since creation (for bench.py's gpu_launches). */
 int64_t hank_launch_count(hank_ctx* ctx);
+/* Per-kernel device times of the four sweep kernels, measured with CUDA events on the ctx stream
+ * while enabled: index 0 backward primal, 1 backward tangent, 2 forward primal, 3 forward tangent.
+ * hank_kernel_times synchronises, returns accumulated milliseconds and launch counts, and
+ * optionally resets the accumulators.                                                        */
+int hank_profile(hank_ctx* ctx, int enable);
+int hank_kernel_times(hank_ctx* ctx, double* ms4, int64_t* count4, int reset);
 /* Max tangent lanes one pass may carry with the memory currently reserved; hank_reserve_lanes
  * grows the reservation (policy tangents are 8*G*P bytes per lane).                          */
 int hank_reserve_lanes(hank_ctx* ctx, int K);

@@ -18,6 +18,23 @@ int cuda_check(hank_ctx* c, cudaError_t e, const char* what) {
   return set_error(c, HANK_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 
+cudaEvent_t prof_begin(hank_ctx* c) {
+  if (!c->profile) return nullptr;
+  cudaEvent_t e = nullptr;
+  if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); }
+  else if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+  cudaEventRecord(e, c->stream);
+  return e;
+}
+void prof_end(hank_ctx* c, int kind, cudaEvent_t a) {
+  if (!c->profile || !a) return;
+  cudaEvent_t e = nullptr;
+  if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); }
+  else if (cudaEventCreate(&e) != cudaSuccess) { c->ev_pool.push_back(a); return; }
+  cudaEventRecord(e, c->stream);
+  c->recs.push_back({kind, a, e});
+}
+
 #define CK(call)                                                   \
   do {                                                             \
     int rc__ = hank::cuda_check(c, (call), #call);                 \
@@ -303,6 +320,8 @@ void hank_ctx_destroy(hank_ctx* c) {
   dfree(c->d_kdpart); dfree(c->d_KD); dfree(c->d_dkdpart); dfree(c->d_dKD); dfree(c->d_status);
   dfree(c->d_x); dfree(c->d_Z); dfree(c->d_F); dfree(c->d_V); dfree(c->d_JV);
   dfree(c->d_Jinv); dfree(c->d_newton); dfree(c->d_newton_i);
+  for (auto& r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto e : c->ev_pool) cudaEventDestroy(e);
   if (c->h_status) cudaFreeHost(c->h_status);
   if (c->h_pin) cudaFreeHost(c->h_pin);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -326,6 +345,28 @@ int hank_timer_stop(hank_ctx* c, float* ms) {
   return HANK_OK;
 }
 int64_t hank_launch_count(hank_ctx* c) { return c ? c->launches : 0; }
+int hank_profile(hank_ctx* c, int enable) {
+  if (!c) return HANK_ERR_ARG;
+  c->profile = enable != 0;
+  return HANK_OK;
+}
+int hank_kernel_times(hank_ctx* c, double* ms4, int64_t* count4, int reset) {
+  if (!c) return HANK_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  for (auto& r : c->recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { c->kern_ms[r.kind] += ms; c->kern_n[r.kind]++; }
+    c->ev_pool.push_back(r.a); c->ev_pool.push_back(r.b);
+  }
+  c->recs.clear();
+  for (int k = 0; k < 4; ++k) {
+    if (ms4) ms4[k] = c->kern_ms[k];
+    if (count4) count4[k] = c->kern_n[k];
+    if (reset) { c->kern_ms[k] = 0; c->kern_n[k] = 0; }
+  }
+  return HANK_OK;
+}
 int hank_reserve_lanes(hank_ctx* c, int K) {
   CK(cudaSetDevice(c->device));
   RC(ensure_lanes(c, K));

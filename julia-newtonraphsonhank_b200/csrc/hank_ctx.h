@@ -48,6 +48,14 @@ struct hank_ctx {
 
   std::string err;
   int64_t launches = 0;
+
+  // per-kernel CUDA-event timing of the sweep kernels (hank_profile / hank_kernel_times)
+  bool profile = false;
+  struct Rec { int kind; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> ev_pool;
+  double kern_ms[4] = {0, 0, 0, 0};
+  int64_t kern_n[4] = {0, 0, 0, 0};
 };
 
 namespace hank {
@@ -75,6 +83,9 @@ struct Sweeps {
   static int lanes_per_cta(hank_ctx* c, int K);
 };
 
+enum { KIND_BP = 0, KIND_BT = 1, KIND_FP = 2, KIND_FT = 3 };
+cudaEvent_t prof_begin(hank_ctx* c);
+void prof_end(hank_ctx* c, int kind, cudaEvent_t a);
 int set_error(hank_ctx* c, int code, const std::string& msg);
 int cuda_check(hank_ctx* c, cudaError_t e, const char* what);
 

@@ -29,12 +29,14 @@ static int set_smem(hank_ctx* c, KernelT k, size_t bytes) {
                     "cudaFuncSetAttribute");
 }
 
-#define HANK_LAUNCH(kern, grid, block, smem, ...)                                   \
+#define HANK_LAUNCH(kind, kern, grid, block, smem, ...)                             \
   do {                                                                              \
     auto kfn_ = kern;                                                               \
     int rc_ = set_smem(c, kfn_, smem);                                              \
     if (rc_) return rc_;                                                            \
+    cudaEvent_t ev_ = prof_begin(c);                                                \
     kfn_<<<grid, block, smem, c->stream>>>(__VA_ARGS__);                            \
+    prof_end(c, kind, ev_);                                                         \
     c->launches++;                                                                  \
     return cuda_check(c, cudaGetLastError(), #kern);                                \
   } while (0)
@@ -45,9 +47,9 @@ static int bp_launch(hank_ctx* c, int P, const double* valueT, const double* r, 
   const Consts<NE> M = make_consts<NE>(c, P);
   const size_t smem = ((size_t)NE * NT * R + NT * R) * sizeof(double);
   if (c->gamma == 2.0)
-    HANK_LAUNCH((k_backward_primal<NE, R, NT, true>), 1, NT, smem, M, c->tape, c->d_grid, valueT, r, w, c->d_status);
+    HANK_LAUNCH(KIND_BP, (k_backward_primal<NE, R, NT, true>), 1, NT, smem, M, c->tape, c->d_grid, valueT, r, w, c->d_status);
   else
-    HANK_LAUNCH((k_backward_primal<NE, R, NT, false>), 1, NT, smem, M, c->tape, c->d_grid, valueT, r, w, c->d_status);
+    HANK_LAUNCH(KIND_BP, (k_backward_primal<NE, R, NT, false>), 1, NT, smem, M, c->tape, c->d_grid, valueT, r, w, c->d_status);
 }
 template <int NE>
 int Sweeps<NE>::backward_primal(hank_ctx* c, int P, const double* valueT, const double* r, const double* w) {
@@ -79,7 +81,7 @@ static int bt_launch(hank_ctx* c, int P, int K, const double* dr, const double* 
   const Consts<NE> M = make_consts<NE>(c, P);
   const size_t smem = (size_t)L * NE * NT * R * sizeof(double);
   const int grid = (K + L - 1) / L;
-  HANK_LAUNCH((k_backward_tangent<NE, R, NT, L>), grid, NT, smem, M, c->tape, K, dr, dw, dvalT, dpol, dvf);
+  HANK_LAUNCH(KIND_BT, (k_backward_tangent<NE, R, NT, L>), grid, NT, smem, M, c->tape, K, dr, dw, dvalT, dpol, dvf);
 }
 template <int NE>
 int Sweeps<NE>::backward_tangent(hank_ctx* c, int P, int K, const double* dr, const double* dw,
@@ -101,7 +103,7 @@ static int fp_launch(hank_ctx* c, int P, const double* D0, const double* pol, do
   const Consts<NE> M = make_consts<NE>(c, P);
   constexpr int LDA = NT * R;
   const size_t smem = ((size_t)2 * CS * LDA + LDA) * sizeof(double) + ((size_t)CS * LDA + (size_t)CS * (LDA + 4)) * sizeof(int);
-  HANK_LAUNCH((k_forward_primal<NE, R, NT, CS>), 1, NT, smem, M, c->tape, c->d_grid, D0, pol, c->d_kdpart, KD, c->d_status);
+  HANK_LAUNCH(KIND_FP, (k_forward_primal<NE, R, NT, CS>), 1, NT, smem, M, c->tape, c->d_grid, D0, pol, c->d_kdpart, KD, c->d_status);
 }
 template <int NE>
 static constexpr int small_cs() { return NE < 4 ? NE : 4; }
@@ -128,7 +130,7 @@ static int ft_launch(hank_ctx* c, int P, int K, const double* pol, const double*
   const Consts<NE> M = make_consts<NE>(c, P);
   const size_t smem = (size_t)2 * L * CS * NT * R * sizeof(double);
   const int grid = (K + L - 1) / L;
-  HANK_LAUNCH((k_forward_tangent<NE, R, NT, L, CS>), grid, NT, smem, M, c->tape, K, pol, dpol, nullptr, dkdpart, nullptr);
+  HANK_LAUNCH(KIND_FT, (k_forward_tangent<NE, R, NT, L, CS>), grid, NT, smem, M, c->tape, K, pol, dpol, nullptr, dkdpart, nullptr);
 }
 template <int NE>
 int Sweeps<NE>::forward_tangent(hank_ctx* c, int P, int K, const double* pol, const double* dpol,

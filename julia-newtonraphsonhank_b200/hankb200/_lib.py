@@ -27,6 +27,8 @@ SIGNATURES = {
     "hank_timer_stop": (C.c_int, [ctx_p, c_fp]),
     "hank_launch_count": (C.c_int64, [ctx_p]),
     "hank_reserve_lanes": (C.c_int, [ctx_p, C.c_int]),
+    "hank_profile": (C.c_int, [ctx_p, C.c_int]),
+    "hank_kernel_times": (C.c_int, [ctx_p, c_dp, C.POINTER(C.c_int64), C.c_int]),
     "hank_set_terminal": (C.c_int, [ctx_p, c_dp]),
     "hank_set_initial_dist": (C.c_int, [ctx_p, c_dp]),
     "hank_egm_step": (C.c_int, [ctx_p, c_dp, c_dp, C.c_double, C.c_double, C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),

@@ -86,6 +86,16 @@ class HouseholdBlock:
     def launch_count(self):
         return int(self._L.hank_launch_count(self._h))
 
+    def profile(self, enable=True):
+        self._ck(self._L.hank_profile(self._h, int(bool(enable))))
+
+    def kernel_times(self, reset=True):
+        """{kernel: (total ms, launches)} of the four sweep kernels since the last reset."""
+        ms = np.zeros(4); cnt = np.zeros(4, dtype=np.int64)
+        self._ck(self._L.hank_kernel_times(self._h, _p(ms), cnt.ctypes.data_as(C.POINTER(C.c_int64)), int(reset)))
+        names = ("backward_primal", "backward_tangent", "forward_primal", "forward_tangent")
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(names)}
+
     def reserve_lanes(self, K):
         self._ck(self._L.hank_reserve_lanes(self._h, int(K)))
 
