@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 #include "hank_ctx.h"
 #include "../../include/hankb200.h"
@@ -160,10 +161,11 @@ static int sw_backward_tangent(hank_ctx* c, int P, int K, const double* dr, cons
 static int sw_forward_primal(hank_ctx* c, int P, const double* D0, const double* pol, double* KD) {
   NE_DISPATCH(c, forward_primal(c, P, D0, pol, KD));
 }
-static int sw_forward_tangent(hank_ctx* c, int P, int K, const double* pol, const double* dpol,
-                              double* dkdpart, int* nw) {
-  NE_DISPATCH(c, forward_tangent(c, P, K, pol, dpol, dkdpart, nw));
+static int sw_forward_tangent(hank_ctx* c, int P, int K, const double* dpol, double* dkdpart, int* nw) {
+  NE_DISPATCH(c, forward_tangent(c, P, K, dpol, dkdpart, nw));
 }
+static inline size_t bw_chunk(const hank_ctx* c) { return (size_t)52 * c->lda; }
+static inline size_t fw_chunk(const hank_ctx* c) { return (size_t)FW_NF * 8 * c->lda + (size_t)4 * (c->lda + 4); }
 
 template <typename T>
 static int dalloc(hank_ctx* c, T** p, size_t count) {
@@ -237,7 +239,7 @@ static int copy_out(hank_ctx* c, T* dst_dense, const T* src_padded, size_t rows)
 static int tangent_pass(hank_ctx* c, int P, int K) {
   RC(sw_backward_tangent(c, P, K, c->d_dr, c->d_dw, nullptr, c->d_dpol, nullptr));
   int nw = 16;
-  RC(sw_forward_tangent(c, P, K, c->tape.pol, c->d_dpol, c->d_dkdpart, &nw));
+  RC(sw_forward_tangent(c, P, K, c->d_dpol, c->d_dkdpart, &nw));
   k_reduce_partials<<<nblk((size_t)K * P), 256, 0, c->stream>>>(c->d_dkdpart, nw, K * P, c->d_dKD);
   c->launches++;
   return cuda_check(c, cudaGetLastError(), "k_reduce_partials");
@@ -281,6 +283,8 @@ int hank_ctx_create(hank_ctx** out, int device, int n_a, int n_e, int T, const d
   Shape s;
   if (!pick_shape(n_a, &s)) return set_error(c, HANK_ERR_ARG, "n_a > 2048 is not supported in this build");
   c->lda = s.NT * s.R; c->Gp = n_e * c->lda;
+  { const char* nt = getenv("HANK_NO_TMA"); c->no_tma = nt && nt[0] == '1'; }
+  { const char* nt = getenv("HANK_NO_WIDE"); c->no_wide = nt && nt[0] == '1'; }
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&c->ev0));
   CK(cudaEventCreate(&c->ev1));
@@ -291,13 +295,10 @@ int hank_ctx_create(hank_ctx** out, int device, int n_a, int n_e, int T, const d
   CK(cudaMemset(c->d_valueT, 0, c->Gp * sizeof(double))); CK(cudaMemset(c->d_D0, 0, c->Gp * sizeof(double)));
   RC(dalloc(c, &c->d_r, c->P)); RC(dalloc(c, &c->d_w, c->P));
   Tape& tp = c->tape;
-  RC(dalloc(c, &tp.pol, PG)); RC(dalloc(c, &tp.bw, PG * BW_NF)); RC(dalloc(c, &tp.idx, PG));
-  RC(dalloc(c, &tp.rho, c->P)); RC(dalloc(c, &tp.fw, PG * FW_NF));
-  RC(dalloc(c, &tp.start, (size_t)c->P * n_e * (c->lda + 4))); RC(dalloc(c, &tp.mbr, PG));
-  RC(dalloc(c, &tp.value_first, c->Gp));
-  CK(cudaMemset(tp.pol, 0, PG * sizeof(double))); CK(cudaMemset(tp.bw, 0, PG * BW_NF * sizeof(double)));
-  CK(cudaMemset(tp.idx, 0, PG * sizeof(int))); CK(cudaMemset(tp.fw, 0, PG * FW_NF * sizeof(double)));
-  CK(cudaMemset(tp.start, 0, (size_t)c->P * n_e * (c->lda + 4) * sizeof(int)));
+  const size_t bwb = (size_t)c->P * n_e * bw_chunk(c), fwb = (size_t)c->P * n_e * fw_chunk(c);
+  RC(dalloc(c, &tp.pol, PG)); RC(dalloc(c, &tp.bw, bwb)); RC(dalloc(c, &tp.rho, c->P)); RC(dalloc(c, &tp.fw, fwb));
+  RC(dalloc(c, &tp.mbr, PG)); RC(dalloc(c, &tp.value_first, c->Gp));
+  CK(cudaMemset(tp.pol, 0, PG * sizeof(double))); CK(cudaMemset(tp.bw, 0, bwb)); CK(cudaMemset(tp.fw, 0, fwb));
   CK(cudaMemset(tp.mbr, 0, PG * sizeof(int))); CK(cudaMemset(tp.value_first, 0, c->Gp * sizeof(double)));
   RC(dalloc(c, &c->d_kdpart, (size_t)c->P * 16)); RC(dalloc(c, &c->d_KD, c->P));
   RC(dalloc(c, &c->d_status, 4));
@@ -314,7 +315,7 @@ void hank_ctx_destroy(hank_ctx* c) {
   hank_comm_destroy(c);
   Tape& tp = c->tape;
   dfree(c->d_grid); dfree(c->d_valueT); dfree(c->d_D0); dfree(c->d_r); dfree(c->d_w);
-  dfree(tp.pol); dfree(tp.bw); dfree(tp.idx); dfree(tp.rho); dfree(tp.fw); dfree(tp.start); dfree(tp.mbr);
+  dfree(tp.pol); dfree(tp.bw); dfree(tp.rho); dfree(tp.fw); dfree(tp.mbr);
   dfree(tp.value_first);
   dfree(c->d_dr); dfree(c->d_dw); dfree(c->d_dpol); dfree(c->d_dvalT); dfree(c->d_dvalue_first);
   dfree(c->d_kdpart); dfree(c->d_KD); dfree(c->d_dkdpart); dfree(c->d_dKD); dfree(c->d_status);
@@ -408,7 +409,7 @@ static int forward_dev(hank_ctx* c, const double* pol, int K, const double* dpol
   c->have_forward = true;
   if (K > 0) {
     int nw = 16;
-    RC(sw_forward_tangent(c, c->P, K, pol, dpol, c->d_dkdpart, &nw));
+    RC(sw_forward_tangent(c, c->P, K, dpol, c->d_dkdpart, &nw));
     k_reduce_partials<<<nblk((size_t)K * c->P), 256, 0, c->stream>>>(c->d_dkdpart, nw, K * c->P, dKD);
     c->launches++;
     CK(cudaGetLastError());
@@ -454,7 +455,9 @@ int hank_forward_policies(hank_ctx* c, const double* policy, int K, const double
   const int P = c->P;
   if (K > 0) { RC(ensure_lanes(c, K)); if (K > c->Kcap) return set_error(c, HANK_ERR_ARG, "K exceeds device memory"); }
   RC(copy_in(c, c->tape.pol, policy, (size_t)P * c->n_e));
-  if (K > 0) RC(copy_in(c, c->d_dpol, dpolicy, (size_t)K * P * c->n_e));
+  for (int l = 0; l < K; ++l)  // caller [K][P][n_e][n_a] -> device [P][n_e][K][lda]
+    CK(cudaMemcpy2DAsync(c->d_dpol + (size_t)l * c->lda, (size_t)K * c->lda * 8, dpolicy + (size_t)l * P * c->G,
+                         (size_t)c->n_a * 8, (size_t)c->n_a * 8, (size_t)P * c->n_e, cudaMemcpyDefault, c->stream));
   c->have_backward = false; c->linearized = false; c->K_last = K;
   RC(forward_dev(c, c->tape.pol, K, c->d_dpol, c->d_KD, c->d_dKD));
   CK(cudaMemcpyAsync(KD, c->d_KD, P * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -497,7 +500,9 @@ int hank_egm_step(hank_ctx* c, const double* value_next, const double* dvalue_ne
   RC(copy_out(c, policy, c->tape.pol, c->n_e));
   if (K > 0) {
     RC(copy_out(c, dvalue, c->d_dvalue_first, (size_t)K * c->n_e));
-    RC(copy_out(c, dpolicy, c->d_dpol, (size_t)K * c->n_e));  // P = 1: lane stride is one padded grid
+    for (int l = 0; l < K; ++l)  // device [1][n_e][K][lda] -> caller [K][n_e][n_a]
+      CK(cudaMemcpy2DAsync(dpolicy + (size_t)l * c->G, (size_t)c->n_a * 8, c->d_dpol + (size_t)l * c->lda,
+                           (size_t)K * c->lda * 8, (size_t)c->n_a * 8, c->n_e, cudaMemcpyDefault, c->stream));
   }
   return check_status(c);
 }
@@ -506,9 +511,10 @@ int hank_egm_step(hank_ctx* c, const double* value_next, const double* dvalue_ne
 int hank_get_policy(hank_ctx* c, int t, int lane, double* out) {
   CK(cudaSetDevice(c->device));
   if (t < 1 || t > c->P || lane < 0 || lane > c->K_last) return set_error(c, HANK_ERR_ARG, "t or lane out of range");
-  const double* src = lane == 0 ? c->tape.pol + (size_t)(t - 1) * c->Gp
-                                : c->d_dpol + ((size_t)(lane - 1) * c->P + (t - 1)) * c->Gp;
-  RC(copy_out(c, out, src, c->n_e));
+  if (lane == 0) RC(copy_out(c, out, (const double*)(c->tape.pol + (size_t)(t - 1) * c->Gp), c->n_e));
+  else  // tangents are [t][e][K][lda]
+    CK(cudaMemcpy2DAsync(out, (size_t)c->n_a * 8, c->d_dpol + ((size_t)(t - 1) * c->n_e * c->K_last + (lane - 1)) * c->lda,
+                         (size_t)c->K_last * c->lda * 8, (size_t)c->n_a * 8, c->n_e, cudaMemcpyDefault, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return HANK_OK;
 }
@@ -516,7 +522,9 @@ int hank_get_dist(hank_ctx* c, int t, double* out) {
   CK(cudaSetDevice(c->device));
   if (!c->have_forward) return set_error(c, HANK_ERR_STATE, "no forward sweep has been run");
   if (t < 1 || t > c->P) return set_error(c, HANK_ERR_ARG, "t out of range");
-  RC(copy_out(c, out, (const double*)(c->tape.fw + ((size_t)(t - 1) * FW_NF + FW_D) * c->Gp), c->n_e));
+  // D_t sits in field FW_D of each column chunk: [t][e][FW_NF][lda]
+  CK(cudaMemcpy2DAsync(out, (size_t)c->n_a * 8, c->tape.fw + (size_t)(t - 1) * c->n_e * fw_chunk(c) + (size_t)FW_D * c->lda * 8,
+                       fw_chunk(c), (size_t)c->n_a * 8, c->n_e, cudaMemcpyDefault, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return HANK_OK;
 }
@@ -587,12 +595,12 @@ int hank_ks_jvp_dev(hank_ctx* c, int K, const double* V, double* JV) {
     k_extract_drdw<<<nblk((size_t)kc * P), 256, 0, c->stream>>>(Vc, P, kc, c->d_dr, c->d_dw);
     c->launches++;
     RC(tangent_pass(c, P, kc));
+    c->K_last = kc;
     k_ks_residual_tangent<<<nblk((size_t)kc * P), 256, 0, c->stream>>>(P, kc, c->alpha, c->ssKS, c->d_x, c->d_Z, Vc,
                                                                       c->d_dKD, JV + (size_t)k0 * n);
     c->launches++;
     CK(cudaGetLastError());
   }
-  c->K_last = std::min(K, c->Kcap);
   return HANK_OK;
 }
 
@@ -650,6 +658,7 @@ int hank_ks_jacobian_columns_dev(hank_ctx* c, int col_begin, int col_end, double
       k_unit_seeds<<<nblk(kc), 256, 0, c->stream>>>(P, kc, d_lane_col, c->d_dr, c->d_dw);
       c->launches++;
       RC(tangent_pass(c, P, kc));
+      c->K_last = kc;
     }
     CK(cudaMemcpyAsync(d_col_lane, col_lane.data() + col_lo, (col_hi - col_lo) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     k_ks_jac_columns<<<nblk((size_t)(col_hi - col_lo) * P), 256, 0, c->stream>>>(
@@ -660,7 +669,6 @@ int hank_ks_jacobian_columns_dev(hank_ctx* c, int col_begin, int col_end, double
     done_cols = col_hi;
   }
   cudaFree(d_lane_col); cudaFree(d_col_lane);
-  c->K_last = std::min(Kh, c->Kcap);
   return HANK_OK;
 }
 

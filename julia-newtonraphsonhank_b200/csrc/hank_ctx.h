@@ -51,6 +51,8 @@ struct hank_ctx {
 
   // per-kernel CUDA-event timing of the sweep kernels (hank_profile / hank_kernel_times)
   bool profile = false;
+  bool no_wide = false;          // HANK_NO_WIDE=1: never use the 256-thread / 6-lane tangent shape
+  bool no_tma = false;           // HANK_NO_TMA=1: use the register-prefetch tangent kernels
   struct Rec { int kind; cudaEvent_t a, b; };
   std::vector<Rec> recs;
   std::vector<cudaEvent_t> ev_pool;
@@ -78,8 +80,7 @@ struct Sweeps {
   static int backward_tangent(hank_ctx* c, int P, int K, const double* dr, const double* dw,
                               const double* dvalT, double* dpol, double* dvalue_first);
   static int forward_primal(hank_ctx* c, int P, const double* D0, const double* pol, double* KD);
-  static int forward_tangent(hank_ctx* c, int P, int K, const double* pol, const double* dpol,
-                             double* dkdpart, int* nw_out);
+  static int forward_tangent(hank_ctx* c, int P, int K, const double* dpol, double* dkdpart, int* nw_out);
   static int lanes_per_cta(hank_ctx* c, int K);
 };
 

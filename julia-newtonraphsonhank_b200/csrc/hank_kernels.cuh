@@ -27,21 +27,36 @@ struct Consts {          // passed by value: lives in the constant bank, indexed
   int n_a, P, gamma_int;         // gamma_int: γ is integer-valued (Julia's integer-power path)
 };
 
-// HBM layout: every per-point array is [t][e][LDA] with the compile-time leading dimension
-// LDA = NT*R >= n_a (256/512/1024/2048), so one base pointer per period plus immediate offsets
-// addresses every (field, e, row) a thread touches — no per-column address registers.
+// HBM layout: every per-point array has the compile-time leading dimension LDA = NT*R >= n_a
+// (256/512/1024/2048).  The tape is stored as ONE CONTIGUOUS CHUNK PER COLUMN (t, e) so that a
+// single TMA bulk copy stages everything the tangent sweep needs for that column:
+//   backward chunk: BW_NF x [LDA] doubles (a1, kr, cA, cB, E1, vf) | [LDA] ints (left knot idx)
+//   forward  chunk: FW_NF x [LDA] doubles (ω, D/Δg, D_t, p_t)      | [LDA+4] ints (range starts)
+// Policy tangents are [t][e][lane][LDA] so the L lanes of a CTA are contiguous per column.
 enum { BW_A1 = 0, BW_KR, BW_CA, BW_CB, BW_E1, BW_VF, BW_NF };   // backward tape fields
-enum { FW_OM = 0, FW_DCO, FW_D, FW_NF };                        // forward tape fields
+enum { FW_OM = 0, FW_DCO, FW_D, FW_P, FW_NF };                  // forward tape fields
+template <int LDA> __host__ __device__ constexpr size_t bw_chunk_bytes() { return (size_t)BW_NF * LDA * 8 + (size_t)LDA * 4; }
+template <int LDA> __host__ __device__ constexpr size_t fw_chunk_bytes() { return (size_t)FW_NF * LDA * 8 + (size_t)(LDA + 4) * 4; }
 struct Tape {
-  double* pol;          // [P][NE][LDA]      policy a'(a,e)
-  double* bw;           // [P][BW_NF][NE][LDA] EGM linearisation
-  int* idx;             // [P][NE][LDA]      left knot of the interpolation interval (0-based)
+  double* pol;          // [P][NE][LDA]   policy a'(a,e)
+  unsigned char* bw;    // [P][NE] backward chunks
   double* rho;          // [P]
-  double* fw;           // [P][FW_NF][NE][LDA] lottery linearisation: ω, D/Δg, D_t
-  int* start;           // [P][NE][LDA+4]    source-range starts per destination row
-  int* mbr;             // [P][NE][LDA]      1-based searchsortedfirst brackets
-  double* value_first;  // [NE][LDA]         ∂V/∂a after the last backward step (t = 1)
+  unsigned char* fw;    // [P][NE] forward chunks
+  int* mbr;             // [P][NE][LDA]   1-based searchsortedfirst brackets
+  double* value_first;  // [NE][LDA]      ∂V/∂a after the last backward step (t = 1)
 };
+template <int LDA> __device__ __forceinline__ double* bw_fields(const Tape& tp, int NE, int t, int e) {
+  return reinterpret_cast<double*>(tp.bw + ((size_t)t * NE + e) * bw_chunk_bytes<LDA>());
+}
+template <int LDA> __device__ __forceinline__ int* bw_idx(const Tape& tp, int NE, int t, int e) {
+  return reinterpret_cast<int*>(tp.bw + ((size_t)t * NE + e) * bw_chunk_bytes<LDA>() + (size_t)BW_NF * LDA * 8);
+}
+template <int LDA> __device__ __forceinline__ double* fw_fields(const Tape& tp, int NE, int t, int e) {
+  return reinterpret_cast<double*>(tp.fw + ((size_t)t * NE + e) * fw_chunk_bytes<LDA>());
+}
+template <int LDA> __device__ __forceinline__ int* fw_start(const Tape& tp, int NE, int t, int e) {
+  return reinterpret_cast<int*>(tp.fw + ((size_t)t * NE + e) * fw_chunk_bytes<LDA>() + (size_t)FW_NF * LDA * 8);
+}
 
 enum { ST_CODE = 0, ST_A = 1, ST_E = 2, ST_T = 3 };
 
@@ -115,9 +130,7 @@ k_backward_primal(const Consts<NE> M, const Tape tp, const double* __restrict__ 
   for (int t = P - 1; t >= 0; --t) {
     const double r = rpath[t], w = wpath[t];
     const double opr = 1.0 + r, rho = 1.0 / opr;
-    double* bwt = tp.bw + (size_t)t * BW_NF * NE * LDA + tid;
     double* polt = tp.pol + (size_t)t * NE * LDA + tid;
-    int* idxt = tp.idx + (size_t)t * NE * LDA + tid;
     if (tid == 0) tp.rho[t] = rho;
     // ---- phase 1: Euler inversion, endogenous grid (KrusellSmith.jl:59-62)
 #pragma unroll
@@ -136,8 +149,8 @@ k_backward_primal(const Consts<NE> M, const Tape tp, const double* __restrict__ 
           const double S = (c - w * M.z[e]) + ga;
           ks[e * LDA + a] = rho * S;
           // ċ = Ḃ·yexp·B^(yexp-1);  k̇ = ρ·(ċ − ẇ z) + S·ρ̇,  ρ̇ = −(ρ/(1+r))·ṙ
-          bwt[(BW_A1 * NE + e) * LDA + j * NT] = rho * (M.beta * (M.yexp * (c / B)));
-          bwt[(BW_KR * NE + e) * LDA + j * NT] = -(S * (rho / opr));
+          bw_fields<LDA>(tp, NE, t, e)[BW_A1 * LDA + j * NT + tid] = rho * (M.beta * (M.yexp * (c / B)));
+          bw_fields<LDA>(tp, NE, t, e)[BW_KR * LDA + j * NT + tid] = -(S * (rho / opr));
         }
       }
     }
@@ -170,16 +183,16 @@ k_backward_primal(const Consts<NE> M, const Tape tp, const double* __restrict__ 
           if (cg < 0.0 && !M.gamma_int) raise(status, 2, a, e, t);
           const double cgp = pow_v<G2>(cg, M.gamma);
           polt[e * LDA + j * NT] = p;
-          idxt[e * LDA + j * NT] = i;
+          bw_idx<LDA>(tp, NE, t, e)[j * NT + tid] = i;
           // δ̇ = (1/den)(−k̇_i) + (−num/den²)(k̇_{i+1} − k̇_i);  q̇ = δ̇ (g_{i+1} − g_i)
           const bool live = interior && !cons;
           const double dg = gi1 - gi, id = 1.0 / den, nd2 = num / (den * den);
-          bwt[(BW_CA * NE + e) * LDA + j * NT] = live ? (nd2 - id) * dg : 0.0;
-          bwt[(BW_CB * NE + e) * LDA + j * NT] = live ? -(nd2 * dg) : 0.0;
+          bw_fields<LDA>(tp, NE, t, e)[BW_CA * LDA + j * NT + tid] = live ? (nd2 - id) * dg : 0.0;
+          bw_fields<LDA>(tp, NE, t, e)[BW_CB * LDA + j * NT + tid] = live ? -(nd2 * dg) : 0.0;
           // V̇ = ṙ·cg^-γ + (1+r)·(−γ)·cg^(−γ−1)·ċg,  ċg = ṙ a + ẇ z − ṗ
           const double vf = opr * ((-M.gamma) * (cgp / cg));
-          bwt[(BW_VF * NE + e) * LDA + j * NT] = vf;
-          bwt[(BW_E1 * NE + e) * LDA + j * NT] = cgp + vf * x;
+          bw_fields<LDA>(tp, NE, t, e)[BW_VF * LDA + j * NT + tid] = vf;
+          bw_fields<LDA>(tp, NE, t, e)[BW_E1 * LDA + j * NT + tid] = cgp + vf * x;
           V[j][e] = opr * cgp;
         }
       }
@@ -192,105 +205,6 @@ k_backward_primal(const Consts<NE> M, const Tape tp, const double* __restrict__ 
     if (a < n_a)
 #pragma unroll
       for (int e = 0; e < NE; ++e) tp.value_first[e * LDA + a] = V[j][e];
-  }
-}
-
-// ======================================================================================
-// Backward tangent sweep: K lanes of ForwardDiff partials through the EGM recursion
-// (SURVEY.md A.3), as a linear recursion with the taped coefficients. CTA b carries lanes
-// [b*L, b*L+L). smem: kds[L][NE][LDA] (k̇ staging for the bracket gather).
-// dr/dw: [K][P]; dvalT: [K][NE][LDA] or null (zero terminal tangents, BackwardIteration.jl:85);
-// dpol: [K][P][NE][LDA].
-// ======================================================================================
-template <int NE, int R, int NT, int L>
-__global__ void __launch_bounds__(NT, 1)
-k_backward_tangent(const Consts<NE> M, const Tape tp, int K, const double* __restrict__ dr,
-                   const double* __restrict__ dw, const double* __restrict__ dvalT,
-                   double* __restrict__ dpol, double* __restrict__ dvalue_first) {
-  constexpr int LDA = NT * R;
-  constexpr size_t GP = (size_t)NE * LDA;
-  extern __shared__ double smem[];
-  const int n_a = M.n_a, P = M.P;
-  const int tid = threadIdx.x;
-  double* kds = smem + tid;
-  const int lane0 = blockIdx.x * L;
-  double Vd[L][R][NE];
-#pragma unroll
-  for (int l = 0; l < L; ++l)
-#pragma unroll
-    for (int j = 0; j < R; ++j) {
-      const int a = tid + j * NT;
-#pragma unroll
-      for (int e = 0; e < NE; ++e)
-        Vd[l][j][e] = (dvalT && a < n_a && lane0 + l < K) ? dvalT[(size_t)(lane0 + l) * GP + e * LDA + a] : 0.0;
-    }
-  for (int t = P - 1; t >= 0; --t) {
-    const double* bwt = tp.bw + (size_t)t * BW_NF * GP + tid;
-    const int* idxt = tp.idx + (size_t)t * GP + tid;
-    const double rho = tp.rho[t];
-    double drl[L], dwl[L];
-#pragma unroll
-    for (int l = 0; l < L; ++l) {
-      const bool on = lane0 + l < K;
-      drl[l] = on ? __ldg(dr + (size_t)(lane0 + l) * P + t) : 0.0;
-      dwl[l] = on ? __ldg(dw + (size_t)(lane0 + l) * P + t) : 0.0;
-    }
-    // ---- phase 1: k̇ = a1·ĖV + kr·ṙ − ρ z ẇ
-#pragma unroll
-    for (int j = 0; j < R; ++j) {
-      if (tid + j * NT < n_a) {
-#pragma unroll
-        for (int e = 0; e < NE; ++e) {
-          const double a1 = __ldg(bwt + (BW_A1 * NE + e) * LDA + j * NT);
-          const double kr = __ldg(bwt + (BW_KR * NE + e) * LDA + j * NT);
-          const double cw = -(rho * M.z[e]);
-#pragma unroll
-          for (int l = 0; l < L; ++l) {
-            double ev = 0.0;
-#pragma unroll
-            for (int e2 = 0; e2 < NE; ++e2) ev = fma(M.Pi[e][e2], Vd[l][j][e2], ev);
-            kds[(l * NE + e) * LDA + j * NT] = fma(a1, ev, fma(kr, drl[l], cw * dwl[l]));
-          }
-        }
-      }
-    }
-    __syncthreads();
-    // ---- phase 2: q̇ from the two bracketing knots, ṗ, V̇
-#pragma unroll
-    for (int j = 0; j < R; ++j) {
-      if (tid + j * NT < n_a) {
-#pragma unroll
-        for (int e = 0; e < NE; ++e) {
-          const int i = __ldg(idxt + e * LDA + j * NT);
-          const double cA = __ldg(bwt + (BW_CA * NE + e) * LDA + j * NT);
-          const double cB = __ldg(bwt + (BW_CB * NE + e) * LDA + j * NT);
-          const double E1 = __ldg(bwt + (BW_E1 * NE + e) * LDA + j * NT);
-          const double vf = __ldg(bwt + (BW_VF * NE + e) * LDA + j * NT);
-          const double ze = M.z[e];
-          const double* kk = smem + i;
-#pragma unroll
-          for (int l = 0; l < L; ++l) {
-            const double pd = fma(cA, kk[(l * NE + e) * LDA], cB * kk[(l * NE + e) * LDA + 1]);
-            if (lane0 + l < K)
-              __stcs(dpol + ((size_t)(lane0 + l) * P + t) * GP + e * LDA + j * NT + tid, pd);
-            Vd[l][j][e] = fma(vf, fma(ze, dwl[l], -pd), E1 * drl[l]);
-          }
-        }
-      }
-    }
-    __syncthreads();
-  }
-  if (dvalue_first) {
-#pragma unroll
-    for (int l = 0; l < L; ++l)
-      if (lane0 + l < K)
-#pragma unroll
-        for (int j = 0; j < R; ++j) {
-          const int a = tid + j * NT;
-          if (a < n_a)
-#pragma unroll
-            for (int e = 0; e < NE; ++e) dvalue_first[(size_t)(lane0 + l) * GP + e * LDA + a] = Vd[l][j][e];
-        }
   }
 }
 
@@ -332,7 +246,6 @@ k_forward_primal(const Consts<NE> M, const Tape tp, const double* __restrict__ g
   __syncthreads();
   for (int t = 0; t < P; ++t) {
     const double* polt = pol_in + (size_t)t * GP + tid;
-    double* fwt = tp.fw + (size_t)t * FW_NF * GP + tid;
     int* mbt = tp.mbr + (size_t)t * GP + tid;
     double tmp[R][NE];
 #pragma unroll
@@ -359,8 +272,9 @@ k_forward_primal(const Consts<NE> M, const Tape tp, const double* __restrict__ g
               X[ee * LDA + a] = om * D[j][e];
               Y[ee * LDA + a] = (1.0 - om) * D[j][e];
               ms[ee * LDA + a] = m;
-              fwt[(FW_OM * NE + e) * LDA + j * NT] = om;
-              fwt[(FW_DCO * NE + e) * LDA + j * NT] = dco;
+              fw_fields<LDA>(tp, NE, t, e)[FW_OM * LDA + j * NT + tid] = om;
+              fw_fields<LDA>(tp, NE, t, e)[FW_DCO * LDA + j * NT + tid] = dco;
+              fw_fields<LDA>(tp, NE, t, e)[FW_P * LDA + j * NT + tid] = p;
               mbt[e * LDA + j * NT] = m;
             }
           }
@@ -398,7 +312,7 @@ k_forward_primal(const Consts<NE> M, const Tape tp, const double* __restrict__ g
             if (e < NE) {
               const int* s = st + ee * NS + a + 1;
               const int s0 = s[0], s1 = s[1], s2 = s[2];
-              int* so = tp.start + ((size_t)t * NE + e) * NS;
+              int* so = fw_start<LDA>(tp, NE, t, e);
               so[a + 1] = s0;
               if (a == n_a - 1) { so[a + 2] = s1; so[a + 3] = s2; }
               double acc = 0.0;
@@ -422,7 +336,7 @@ k_forward_primal(const Consts<NE> M, const Tape tp, const double* __restrict__ g
 #pragma unroll
           for (int e = 0; e < NE; ++e) d += M.Pi[e][e2] * tmp[j][e];
           D[j][e2] = d;
-          fwt[(FW_D * NE + e2) * LDA + j * NT] = d;
+          fw_fields<LDA>(tp, NE, t, e2)[FW_D * LDA + j * NT + tid] = d;
           kacc += polt[e2 * LDA + j * NT] * d;
         }
       }
@@ -435,133 +349,6 @@ k_forward_primal(const Consts<NE> M, const Tape tp, const double* __restrict__ g
     double s = 0.0;
     for (int wv = 0; wv < NW; ++wv) s += kdpart[(size_t)t * NW + wv];
     KD[t] = s;
-  }
-}
-
-// ======================================================================================
-// Forward tangent sweep: Ḋ recursion and K̇D_t = <ṗ_t, D_t> + <p_t, Ḋ_t> for L lanes per CTA
-// (SURVEY.md A.4 tangent rules).  smem: Xd[L][CS][LDA] | Yd[L][CS][LDA]
-// dkdpart: [K][P][NT/32]
-// ======================================================================================
-template <int NE, int R, int NT, int L, int CS>
-__global__ void __launch_bounds__(NT, 1)
-k_forward_tangent(const Consts<NE> M, const Tape tp, int K, const double* __restrict__ pol_in,
-                  const double* __restrict__ dpol, const double* __restrict__ dD0,
-                  double* __restrict__ dkdpart, double* __restrict__ dD_last) {
-  constexpr int LDA = NT * R, NS = LDA + 4;
-  constexpr size_t GP = (size_t)NE * LDA;
-  extern __shared__ double smem[];
-  const int n_a = M.n_a, P = M.P;
-  double* Xd = smem;
-  double* Yd = smem + (size_t)L * CS * LDA;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int NW = NT / 32;
-  const int lane0 = blockIdx.x * L;
-  double Dd[L][R][NE];
-#pragma unroll
-  for (int l = 0; l < L; ++l)
-#pragma unroll
-    for (int j = 0; j < R; ++j) {
-      const int a = tid + j * NT;
-#pragma unroll
-      for (int e = 0; e < NE; ++e)
-        Dd[l][j][e] = (dD0 && a < n_a && lane0 + l < K) ? dD0[(size_t)(lane0 + l) * GP + e * LDA + a] : 0.0;
-    }
-  for (int t = 0; t < P; ++t) {
-    const double* fwt = tp.fw + (size_t)t * FW_NF * GP + tid;
-    const double* polt = pol_in + (size_t)t * GP + tid;
-    double kacc[L];
-#pragma unroll
-    for (int l = 0; l < L; ++l) kacc[l] = 0.0;
-    double tmp[L][R][NE];
-#pragma unroll
-    for (int e0 = 0; e0 < NE; e0 += CS) {
-      // ---- phase A: ẋ = ω Ḋ + (D/Δg) ṗ,  ẏ = Ḋ − ẋ;  first aggregation term <ṗ_t, D_t>
-#pragma unroll
-      for (int j = 0; j < R; ++j) {
-        if (tid + j * NT < n_a) {
-#pragma unroll
-          for (int ee = 0; ee < CS; ++ee) {
-            const int e = e0 + ee;
-            if (e < NE) {
-              const double om = __ldg(fwt + (FW_OM * NE + e) * LDA + j * NT);
-              const double dco = __ldg(fwt + (FW_DCO * NE + e) * LDA + j * NT);
-              const double Dn = __ldg(fwt + (FW_D * NE + e) * LDA + j * NT);
-#pragma unroll
-              for (int l = 0; l < L; ++l) {
-                const double pd = (lane0 + l < K)
-                    ? __ldcs(dpol + ((size_t)(lane0 + l) * P + t) * GP + e * LDA + j * NT + tid) : 0.0;
-                const double xd = fma(om, Dd[l][j][e], dco * pd);
-                Xd[(l * CS + ee) * LDA + j * NT + tid] = xd;
-                Yd[(l * CS + ee) * LDA + j * NT + tid] = Dd[l][j][e] - xd;
-                kacc[l] = fma(pd, Dn, kacc[l]);
-              }
-            }
-          }
-        }
-      }
-      __syncthreads();
-      // ---- phase C: gather over the taped source ranges
-#pragma unroll
-      for (int j = 0; j < R; ++j) {
-        const int a = tid + j * NT;
-        if (a < n_a) {
-#pragma unroll
-          for (int ee = 0; ee < CS; ++ee) {
-            const int e = e0 + ee;
-            if (e < NE) {
-              const int* s = tp.start + ((size_t)t * NE + e) * NS + a + 1;
-              const int s0 = __ldg(s), s1 = __ldg(s + 1), s2 = __ldg(s + 2);
-#pragma unroll
-              for (int l = 0; l < L; ++l) {
-                const double* xs = Xd + (l * CS + ee) * LDA;
-                const double* ys = Yd + (l * CS + ee) * LDA;
-                double acc = 0.0;
-                for (int b = s0; b < s1; ++b) acc += xs[b];
-                for (int b = s1; b < s2; ++b) acc += ys[b];
-                tmp[l][j][e] = acc;
-              }
-            }
-          }
-        }
-      }
-      __syncthreads();
-    }
-    // ---- Markov mix and second aggregation term <p_t, Ḋ_t>
-#pragma unroll
-    for (int j = 0; j < R; ++j) {
-      if (tid + j * NT < n_a) {
-#pragma unroll
-        for (int e2 = 0; e2 < NE; ++e2) {
-          const double p = __ldg(polt + e2 * LDA + j * NT);
-#pragma unroll
-          for (int l = 0; l < L; ++l) {
-            double d = 0.0;
-#pragma unroll
-            for (int e = 0; e < NE; ++e) d = fma(M.Pi[e][e2], tmp[l][j][e], d);
-            Dd[l][j][e2] = d;
-            kacc[l] = fma(p, d, kacc[l]);
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int l = 0; l < L; ++l) {
-      const double s = warp_sum(kacc[l]);
-      if (lane == 0 && lane0 + l < K) dkdpart[((size_t)(lane0 + l) * P + t) * NW + warp] = s;
-    }
-  }
-  if (dD_last) {
-#pragma unroll
-    for (int l = 0; l < L; ++l)
-      if (lane0 + l < K)
-#pragma unroll
-        for (int j = 0; j < R; ++j) {
-          const int a = tid + j * NT;
-          if (a < n_a)
-#pragma unroll
-            for (int e = 0; e < NE; ++e) dD_last[(size_t)(lane0 + l) * GP + e * LDA + a] = Dd[l][j][e];
-        }
   }
 }
 

@@ -5,6 +5,8 @@
 #include <cmath>
 #include <cstdio>
 #include "hank_ctx.h"
+#include "hank_tangent.cuh"
+#include "hank_tangent_tma.cuh"
 
 namespace hank {
 
@@ -61,42 +63,6 @@ int Sweeps<NE>::backward_primal(hank_ctx* c, int P, const double* valueT, const 
   return bp_launch<NE, 4, 512>(c, P, valueT, r, w);
 }
 
-// ---- lanes per CTA ---------------------------------------------------------------------
-// L*R <= 4 (register budget: L*R*NE doubles of state per thread), k̇ staging L*G*8 B must fit.
-template <int NE>
-int Sweeps<NE>::lanes_per_cta(hank_ctx* c, int K) {
-  Shape s;
-  if (!pick_shape(c->n_a, &s)) return 0;
-  int L = 4 / s.R;
-  while (L > 1 && (size_t)L * NE * c->lda * sizeof(double) > (size_t)c->smem_max) L >>= 1;
-  // fill the SMs before deepening the lanes per CTA
-  while (L > 1 && K < c->sm_count * L) L >>= 1;
-  return L;
-}
-
-// ---- backward tangent ------------------------------------------------------------------
-template <int NE, int R, int NT, int L>
-static int bt_launch(hank_ctx* c, int P, int K, const double* dr, const double* dw, const double* dvalT,
-                     double* dpol, double* dvf) {
-  const Consts<NE> M = make_consts<NE>(c, P);
-  const size_t smem = (size_t)L * NE * NT * R * sizeof(double);
-  const int grid = (K + L - 1) / L;
-  HANK_LAUNCH(KIND_BT, (k_backward_tangent<NE, R, NT, L>), grid, NT, smem, M, c->tape, K, dr, dw, dvalT, dpol, dvf);
-}
-template <int NE>
-int Sweeps<NE>::backward_tangent(hank_ctx* c, int P, int K, const double* dr, const double* dw,
-                                 const double* dvalT, double* dpol, double* dvf) {
-  Shape s;
-  if (!pick_shape(c->n_a, &s)) return set_error(c, 1, "n_a > 2048 is not supported");
-  const int L = lanes_per_cta(c, K);
-#define BT(R_, NT_, L_) return bt_launch<NE, R_, NT_, L_>(c, P, K, dr, dw, dvalT, dpol, dvf)
-  if (s.NT == 256) { if (L == 4) BT(1, 256, 4); if (L == 2) BT(1, 256, 2); BT(1, 256, 1); }
-  if (s.R == 1) { if (L == 4) BT(1, 512, 4); if (L == 2) BT(1, 512, 2); BT(1, 512, 1); }
-  if (s.R == 2) { if (L == 2) BT(2, 512, 2); BT(2, 512, 1); }
-  BT(4, 512, 1);
-#undef BT
-}
-
 // ---- forward primal --------------------------------------------------------------------
 template <int NE, int R, int NT, int CS>
 static int fp_launch(hank_ctx* c, int P, const double* D0, const double* pol, double* KD) {
@@ -124,32 +90,99 @@ int Sweeps<NE>::forward_primal(hank_ctx* c, int P, const double* D0, const doubl
 #undef FP
 }
 
-// ---- forward tangent -------------------------------------------------------------------
-template <int NE, int R, int NT, int L, int CS>
-static int ft_launch(hank_ctx* c, int P, int K, const double* pol, const double* dpol, double* dkdpart) {
-  const Consts<NE> M = make_consts<NE>(c, P);
-  const size_t smem = (size_t)2 * L * CS * NT * R * sizeof(double);
-  const int grid = (K + L - 1) / L;
-  HANK_LAUNCH(KIND_FT, (k_forward_tangent<NE, R, NT, L, CS>), grid, NT, smem, M, c->tape, K, pol, dpol, nullptr, dkdpart, nullptr);
+// ---- tangent kernels: (NT, R, L) by leading dimension and lane count ---------------------
+// The register file bounds the lanes a CTA can carry (state = L*R*NE doubles per thread):
+// 512 threads x R rows hold L*R <= 4; 256 threads x 2R rows hold 6 lanes at LDA 512 (3 at 1024),
+// which cuts the tape bytes staged per lane by a third.  Deeper lanes are only used once every SM
+// has a CTA.
+struct TangentCfg { int NT, R, L; };
+static TangentCfg tangent_cfg(const hank_ctx* c, int K) {
+  const int sm = c->sm_count;
+  switch (c->lda) {
+    case 256: return {256, 1, K >= 4 * sm ? 4 : (K >= 2 * sm ? 2 : 1)};
+    case 512:
+      if (K >= 6 * sm && !c->no_wide) return {256, 2, 6};
+      return {512, 1, K >= 4 * sm ? 4 : (K >= 2 * sm ? 2 : 1)};
+    case 1024:
+      if (K >= 3 * sm && !c->no_wide) return {256, 4, 3};
+      return {512, 2, K >= 2 * sm ? 2 : 1};
+    default: return {512, 4, 1};
+  }
 }
 template <int NE>
-int Sweeps<NE>::forward_tangent(hank_ctx* c, int P, int K, const double* pol, const double* dpol,
-                                double* dkdpart, int* nw_out) {
-  Shape s;
-  if (!pick_shape(c->n_a, &s)) return set_error(c, 1, "n_a > 2048 is not supported");
-  *nw_out = s.NT / 32;
-  const int L = lanes_per_cta(c, K);
-  const bool fits = (size_t)2 * L * NE * c->lda * 8 <= (size_t)c->smem_max;
-  constexpr int C4 = small_cs<NE>();
-  if (!fits && (size_t)2 * L * C4 * c->lda * 8 > (size_t)c->smem_max)
-    return set_error(c, 1, "forward tangent staging does not fit in shared memory");
-#define FT(R_, NT_, L_) do { if (fits) return ft_launch<NE, R_, NT_, L_, NE>(c, P, K, pol, dpol, dkdpart); \
-                             return ft_launch<NE, R_, NT_, L_, C4>(c, P, K, pol, dpol, dkdpart); } while (0)
-  if (s.NT == 256) { if (L == 4) FT(1, 256, 4); if (L == 2) FT(1, 256, 2); FT(1, 256, 1); }
-  if (s.R == 1) { if (L == 4) FT(1, 512, 4); if (L == 2) FT(1, 512, 2); FT(1, 512, 1); }
-  if (s.R == 2) { if (L == 2) FT(2, 512, 2); FT(2, 512, 1); }
-  FT(4, 512, 1);
-#undef FT
+int Sweeps<NE>::lanes_per_cta(hank_ctx* c, int K) { return tangent_cfg(c, K).L; }
+
+template <int NE, int R, int NT, int L>
+static int bt_launch(hank_ctx* c, int P, int K, const double* dr, const double* dw, const double* dvalT,
+                     double* dpol, double* dvf) {
+  const Consts<NE> M = make_consts<NE>(c, P);
+  const int grid = (K + L - 1) / L;
+  constexpr int LDA = NT * R;
+  if (LDA <= 1024 && !c->no_tma) {  // TMA-staged tape ring (hank_tangent_tma.cuh)
+    const size_t slot = bw_chunk_bytes<LDA>();
+    const size_t fixed = (size_t)2 * L * LDA * 8 + (size_t)2 * L * P * 8 + (size_t)((P + 1) & ~1) * 8 + 16 * 8 + 128;
+    int S = fixed < (size_t)c->smem_max ? (int)(((size_t)c->smem_max - fixed) / slot) : 0;
+    if (S > 8) S = 8;
+    if (S >= 2) {
+      const size_t smem_t = fixed + (size_t)S * slot;
+      HANK_LAUNCH(KIND_BT, (k_backward_tangent_tma<NE, R, NT, L>), grid, NT, smem_t, M, c->tape, K, S, dr, dw, dvalT, dpol, dvf);
+    }
+  }
+  const size_t smem = (size_t)2 * L * LDA * sizeof(double);
+  HANK_LAUNCH(KIND_BT, (k_backward_tangent<NE, R, NT, L>), grid, NT, smem, M, c->tape, K, dr, dw, dvalT, dpol, dvf);
+}
+template <int NE, int R, int NT, int L>
+static int ft_launch(hank_ctx* c, int P, int K, const double* dpol, double* dkdpart) {
+  const Consts<NE> M = make_consts<NE>(c, P);
+  const int grid = (K + L - 1) / L;
+  constexpr int LDA = NT * R;
+  if (LDA <= 1024 && !c->no_tma) {
+    const size_t slot = fw_chunk_bytes<LDA>() + (size_t)L * LDA * 8;
+    const size_t fixed = (size_t)4 * L * LDA * 8 + 16 * 8 + 128;
+    int S = fixed < (size_t)c->smem_max ? (int)(((size_t)c->smem_max - fixed) / slot) : 0;
+    if (S > 8) S = 8;
+    if (S >= 2) {
+      const size_t smem_t = fixed + (size_t)S * slot;
+      HANK_LAUNCH(KIND_FT, (k_forward_tangent_tma<NE, R, NT, L>), grid, NT, smem_t, M, c->tape, K, S, dpol, nullptr, dkdpart, nullptr);
+    }
+  }
+  const size_t smem = (size_t)4 * L * LDA * sizeof(double);
+  HANK_LAUNCH(KIND_FT, (k_forward_tangent<NE, R, NT, L>), grid, NT, smem, M, c->tape, K, dpol, nullptr, dkdpart, nullptr);
+}
+
+#define TANGENT_DISPATCH(FN, ...)                                                         \
+  do {                                                                                    \
+    const TangentCfg g = tangent_cfg(c, K);                                               \
+    if (g.NT == 256 && g.R == 1) {                                                        \
+      if (g.L == 4) return FN<NE, 1, 256, 4>(__VA_ARGS__);                                \
+      if (g.L == 2) return FN<NE, 1, 256, 2>(__VA_ARGS__);                                \
+      return FN<NE, 1, 256, 1>(__VA_ARGS__);                                              \
+    }                                                                                     \
+    if (g.NT == 256 && g.R == 2) return FN<NE, 2, 256, 6>(__VA_ARGS__);                   \
+    if (g.NT == 256 && g.R == 4) return FN<NE, 4, 256, 3>(__VA_ARGS__);                   \
+    if (g.R == 1) {                                                                       \
+      if (g.L == 4) return FN<NE, 1, 512, 4>(__VA_ARGS__);                                \
+      if (g.L == 2) return FN<NE, 1, 512, 2>(__VA_ARGS__);                                \
+      return FN<NE, 1, 512, 1>(__VA_ARGS__);                                              \
+    }                                                                                     \
+    if (g.R == 2) {                                                                       \
+      if (g.L == 2) return FN<NE, 2, 512, 2>(__VA_ARGS__);                                \
+      return FN<NE, 2, 512, 1>(__VA_ARGS__);                                              \
+    }                                                                                     \
+    return FN<NE, 4, 512, 1>(__VA_ARGS__);                                                \
+  } while (0)
+
+template <int NE>
+int Sweeps<NE>::backward_tangent(hank_ctx* c, int P, int K, const double* dr, const double* dw,
+                                 const double* dvalT, double* dpol, double* dvf) {
+  if (c->lda > 2048) return set_error(c, 1, "n_a > 2048 is not supported");
+  TANGENT_DISPATCH(bt_launch, c, P, K, dr, dw, dvalT, dpol, dvf);
+}
+template <int NE>
+int Sweeps<NE>::forward_tangent(hank_ctx* c, int P, int K, const double* dpol, double* dkdpart, int* nw_out) {
+  if (c->lda > 2048) return set_error(c, 1, "n_a > 2048 is not supported");
+  *nw_out = tangent_cfg(c, K).NT / 32;
+  TANGENT_DISPATCH(ft_launch, c, P, K, dpol, dkdpart);
 }
 
 }  // namespace hank

@@ -1,0 +1,339 @@
+// hank_tangent_tma.cuh — tangent-lane sweeps with the primal tape (and, in the forward sweep, the
+// policy-tangent stream itself) staged through a shared-memory ring by the TMA bulk-copy engine.
+//
+// Why: the sweeps are chains of dependent periods.  With plain loads every column of every period
+// paid a DRAM/L2 round trip (measured 1000-2000 cycles per column), which capped the first
+// kernels at 27 % / 12 % of the HBM roofline (profiles/r01_notes.md).  Here ONE `cp.async.bulk`
+// copy per column (two in the forward sweep; SASS UBLKCP — the tape is laid out as one contiguous
+// chunk per column for exactly this purpose) is issued several columns ahead, by lane 0 of a
+// different warp each column so the issue cost is spread.  Completion is tracked by one mbarrier
+// per ring slot (`mbarrier.arrive.expect_tx` / `complete_tx`); the per-column __syncthreads() the
+// algorithm needs anyway doubles as the "slot is free" signal, so no second barrier set and no
+// extra producer warp (which would cost 24 registers per thread at 512+32 threads) is needed.
+// Compute threads never issue a global load inside the period loop.
+#pragma once
+#include "hank_tangent.cuh"
+
+namespace hank {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a lost copy must trap instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
+// ======================================================================================
+// Backward tangent sweep, TMA-staged tape.
+// smem: ring[S][bw chunk] | kb[2][L][LDA] | drs[L][P] | dws[L][P] | rhos[P] | full[S]
+// Slot c%S is read in both phases of column c, so it is free after the barrier of column c+1:
+// chunk c+S-1 is issued there (prefetch distance S-1 columns).
+// ======================================================================================
+template <int NE, int R, int NT, int L>
+__global__ void __launch_bounds__(NT, 1)
+k_backward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int S, const double* __restrict__ dr,
+                       const double* __restrict__ dw, const double* __restrict__ dvalT,
+                       double* __restrict__ dpol, double* __restrict__ dvalue_first) {
+  constexpr int LDA = NT * R, NW = NT / 32;
+  constexpr size_t GP = (size_t)NE * LDA;
+  constexpr int CH = (int)bw_chunk_bytes<LDA>();
+  constexpr int SLOT_D = CH / 8;
+  extern __shared__ __align__(128) unsigned char smem_tma[];
+  const int n_a = M.n_a, P = M.P;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lane0 = blockIdx.x * L;
+  double* ring = reinterpret_cast<double*>(smem_tma);
+  double* kbuf = ring + (size_t)S * SLOT_D;
+  double* drs = kbuf + 2 * L * LDA;
+  double* dws = drs + (size_t)L * P;
+  double* rhos = dws + (size_t)L * P;
+  uint64_t* full = reinterpret_cast<uint64_t*>(rhos + ((P + 1) & ~1));
+  const int nchunks = P * NE;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  for (int i = tid; i < L * P; i += NT) {
+    const int l = i / P, t = i - l * P;
+    const bool on = lane0 + l < K;
+    drs[i] = on ? dr[(size_t)(lane0 + l) * P + t] : 0.0;
+    dws[i] = on ? dw[(size_t)(lane0 + l) * P + t] : 0.0;
+  }
+  for (int t = tid; t < P; t += NT) rhos[t] = tp.rho[t];
+  __syncthreads();
+  // chunk c lives at tape.bw + ((P-1-c/NE)*NE + c%NE)*CH
+  if (tid == 0)
+    for (int c = 0; c < S - 1 && c < nchunks; ++c) {
+      mbar_expect_tx(&full[c], CH);
+      bulk_g2s(ring + (size_t)c * SLOT_D, tp.bw + ((size_t)(P - 1 - c / NE) * NE + c % NE) * CH, CH, &full[c]);
+    }
+  // issue cursor (used by whichever thread issues): chunk ci -> (ti, ei), slot si
+  int ci = S - 1, ti = P - 1 - (S - 1) / NE, ei = (S - 1) % NE, si = S - 1;
+
+  bool rowok[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) rowok[j] = tid + j * NT < n_a;
+  double Vd[L][R][NE];
+#pragma unroll
+  for (int l = 0; l < L; ++l)
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+#pragma unroll
+      for (int e = 0; e < NE; ++e)
+        Vd[l][j][e] = (dvalT && rowok[j] && lane0 + l < K)
+            ? dvalT[(size_t)(lane0 + l) * GP + e * LDA + j * NT + tid] : 0.0;
+
+  int slot = 0, par = 0, pb = 0, iw = 0;
+  for (int t = P - 1; t >= 0; --t) {
+    const double rho = rhos[t];
+    double drl[L], dwl[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) { drl[l] = drs[l * P + t]; dwl[l] = dws[l * P + t]; }
+    // ---- phase 0 (registers only): ĖV in place of V̇⁺
+#pragma unroll
+    for (int l = 0; l < L; ++l)
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        double ev[NE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+          double s = 0.0;
+#pragma unroll
+          for (int e2 = 0; e2 < NE; ++e2) s = fma(M.Pi[e][e2], Vd[l][j][e2], s);
+          ev[e] = s;
+        }
+#pragma unroll
+        for (int e = 0; e < NE; ++e) Vd[l][j][e] = ev[e];
+      }
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const double* sl = ring + (size_t)slot * SLOT_D + tid;
+      const int* sli = reinterpret_cast<const int*>(ring + (size_t)slot * SLOT_D + BW_NF * LDA) + tid;
+      double* kb = kbuf + (size_t)pb * L * LDA;
+      mbar_wait(&full[slot], par);
+      const double cw = -(rho * M.z[e]);
+#pragma unroll
+      for (int j = 0; j < R; ++j)
+        if (rowok[j]) {
+          const double a1 = sl[BW_A1 * LDA + j * NT], kr = sl[BW_KR * LDA + j * NT];
+#pragma unroll
+          for (int l = 0; l < L; ++l)
+            kb[l * LDA + j * NT + tid] = fma(a1, Vd[l][j][e], fma(kr, drl[l], cw * dwl[l]));
+        }
+      __syncthreads();
+      // every thread has finished reading the previous column's slot: refill it S-1 columns ahead
+      if (ci < nchunks) {
+        if (warp == iw && lane == 0) {
+          mbar_expect_tx(&full[si], CH);
+          bulk_g2s(ring + (size_t)si * SLOT_D, tp.bw + ((size_t)ti * NE + ei) * CH, CH, &full[si]);
+        }
+        ++ci;
+        if (++ei == NE) { ei = 0; --ti; }
+        if (++si == S) si = 0;
+        if (++iw == NW) iw = 0;
+      }
+      const double ze = M.z[e];
+      double* dpc = dpol + (((size_t)t * NE + e) * K + lane0) * LDA + tid;
+#pragma unroll
+      for (int j = 0; j < R; ++j)
+        if (rowok[j]) {
+          const double cA = sl[BW_CA * LDA + j * NT], cB = sl[BW_CB * LDA + j * NT];
+          const double E1 = sl[BW_E1 * LDA + j * NT], vf = sl[BW_VF * LDA + j * NT];
+          const double* kk = kb + sli[j * NT];
+#pragma unroll
+          for (int l = 0; l < L; ++l) {
+            const double pd = fma(cA, kk[l * LDA], cB * kk[l * LDA + 1]);
+            if (lane0 + l < K) __stcs(dpc + (size_t)l * LDA + j * NT, pd);
+            Vd[l][j][e] = fma(vf, fma(ze, dwl[l], -pd), E1 * drl[l]);
+          }
+        }
+      pb ^= 1;
+      if (++slot == S) { slot = 0; par ^= 1; }
+    }
+  }
+  if (dvalue_first) {
+#pragma unroll
+    for (int l = 0; l < L; ++l)
+      if (lane0 + l < K)
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          if (rowok[j])
+#pragma unroll
+            for (int e = 0; e < NE; ++e)
+              dvalue_first[(size_t)(lane0 + l) * GP + e * LDA + j * NT + tid] = Vd[l][j][e];
+  }
+}
+
+// ======================================================================================
+// Forward tangent sweep, TMA-staged tape and ṗ stream.  Slot = forward chunk | ṗ of L lanes.
+// smem: ring[S][fw chunk + L*LDA doubles] | Xb[2][L][LDA] | Yb[2][L][LDA] | full[S]
+// A slot is only read before the column's barrier, so it is free right after it: chunk c+S is
+// issued after the barrier of column c (prefetch distance S columns).
+// ======================================================================================
+template <int NE, int R, int NT, int L>
+__global__ void __launch_bounds__(NT, 1)
+k_forward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int S, const double* __restrict__ dpol,
+                      const double* __restrict__ dD0, double* __restrict__ dkdpart,
+                      double* __restrict__ dD_last) {
+  constexpr int LDA = NT * R, U = 2, NW = NT / 32;
+  constexpr size_t GP = (size_t)NE * LDA;
+  constexpr int CH = (int)fw_chunk_bytes<LDA>();
+  constexpr int PD_OFF = CH / 8;                 // ṗ lanes follow the chunk (CH is a multiple of 16)
+  constexpr int SLOT_D = PD_OFF + L * LDA;
+  extern __shared__ __align__(128) unsigned char smem_tma[];
+  const int n_a = M.n_a, P = M.P;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lane0 = blockIdx.x * L;
+  double* ring = reinterpret_cast<double*>(smem_tma);
+  double* Xb = ring + (size_t)S * SLOT_D;
+  double* Yb = Xb + 2 * L * LDA;
+  uint64_t* full = reinterpret_cast<uint64_t*>(Yb + 2 * L * LDA);
+  const int nchunks = P * NE;
+  int nl = K - lane0;  // live lanes of this CTA
+  if (nl > L) nl = L;
+  const uint32_t pd_bytes = (uint32_t)(nl * LDA * 8);
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // lanes beyond K read zeros from their (never filled) ṗ slots
+  for (int i = tid; i < S * SLOT_D; i += NT) ring[i] = 0.0;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  auto issue = [&](int t, int e, int s) {
+    double* dst = ring + (size_t)s * SLOT_D;
+    mbar_expect_tx(&full[s], (uint32_t)CH + pd_bytes);
+    bulk_g2s(dst, tp.fw + ((size_t)t * NE + e) * CH, CH, &full[s]);
+    bulk_g2s(dst + PD_OFF, dpol + (((size_t)t * NE + e) * K + lane0) * LDA, pd_bytes, &full[s]);
+  };
+  if (tid == 0)
+    for (int c = 0; c < S && c < nchunks; ++c) issue(c / NE, c % NE, c);
+  int ci = S, ti = S / NE, ei = S % NE, si = 0;
+
+  bool rowok[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) rowok[j] = tid + j * NT < n_a;
+  double Dd[L][R][NE];
+#pragma unroll
+  for (int l = 0; l < L; ++l)
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+#pragma unroll
+      for (int e = 0; e < NE; ++e)
+        Dd[l][j][e] = (dD0 && rowok[j] && lane0 + l < K) ? dD0[(size_t)(lane0 + l) * GP + e * LDA + j * NT + tid] : 0.0;
+
+  int slot = 0, par = 0, pb = 0, iw = 0;
+  for (int t = 0; t < P; ++t) {
+    double kacc[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) kacc[l] = 0.0;
+    double pv[R][NE];  // p_t of the row, picked up column by column for <p_t, Ḋ_t>
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const double* sl = ring + (size_t)slot * SLOT_D + tid;
+      const int* sst = reinterpret_cast<const int*>(ring + (size_t)slot * SLOT_D + FW_NF * LDA) + tid + 1;
+      double* xb = Xb + (size_t)pb * L * LDA;
+      double* yb = Yb + (size_t)pb * L * LDA;
+      mbar_wait(&full[slot], par);
+      int s0[R], s1[R], s2[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        s0[j] = s1[j] = s2[j] = 0;
+        pv[j][e] = 0.0;
+        if (rowok[j]) {
+          const double om = sl[FW_OM * LDA + j * NT], dco = sl[FW_DCO * LDA + j * NT], Dn = sl[FW_D * LDA + j * NT];
+          pv[j][e] = sl[FW_P * LDA + j * NT];
+          s0[j] = sst[j * NT]; s1[j] = sst[j * NT + 1]; s2[j] = sst[j * NT + 2];
+#pragma unroll
+          for (int l = 0; l < L; ++l) {
+            const double pd = sl[PD_OFF + l * LDA + j * NT];
+            const double xd = fma(om, Dd[l][j][e], dco * pd);
+            xb[l * LDA + j * NT + tid] = xd;
+            yb[l * LDA + j * NT + tid] = Dd[l][j][e] - xd;
+            kacc[l] = fma(pd, Dn, kacc[l]);
+          }
+        }
+      }
+      __syncthreads();
+      if (ci < nchunks) {   // this column's slot is free again: refill it S columns ahead
+        if (warp == iw && lane == 0) issue(ti, ei, si);
+        ++ci;
+        if (++ei == NE) { ei = 0; ++ti; }
+        if (++si == S) si = 0;
+        if (++iw == NW) iw = 0;
+      }
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        double acc[L];
+        gather_row<L, LDA, U>(xb, yb, s0[j], s1[j], s2[j], lane, acc);
+#pragma unroll
+        for (int l = 0; l < L; ++l) Dd[l][j][e] = acc[l];
+      }
+      pb ^= 1;
+      if (++slot == S) { slot = 0; par ^= 1; }
+    }
+    // ---- Markov mix (in place) and second aggregation term <p_t, Ḋ_t>
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+      if (rowok[j]) {
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+          double d[NE];
+#pragma unroll
+          for (int e2 = 0; e2 < NE; ++e2) {
+            double s = 0.0;
+#pragma unroll
+            for (int e = 0; e < NE; ++e) s = fma(M.Pi[e][e2], Dd[l][j][e], s);
+            d[e2] = s;
+          }
+#pragma unroll
+          for (int e2 = 0; e2 < NE; ++e2) { Dd[l][j][e2] = d[e2]; kacc[l] = fma(pv[j][e2], d[e2], kacc[l]); }
+        }
+      }
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      const double s = warp_sum(kacc[l]);
+      if (lane == 0 && lane0 + l < K) dkdpart[((size_t)(lane0 + l) * P + t) * NW + warp] = s;
+    }
+  }
+  if (dD_last) {
+#pragma unroll
+    for (int l = 0; l < L; ++l)
+      if (lane0 + l < K)
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          if (rowok[j])
+#pragma unroll
+            for (int e = 0; e < NE; ++e)
+              dD_last[(size_t)(lane0 + l) * GP + e * LDA + j * NT + tid] = Dd[l][j][e];
+  }
+}
+
+}  // namespace hank
