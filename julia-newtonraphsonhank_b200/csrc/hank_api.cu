@@ -285,6 +285,7 @@ int hank_ctx_create(hank_ctx** out, int device, int n_a, int n_e, int T, const d
   c->lda = s.NT * s.R; c->Gp = n_e * c->lda;
   { const char* nt = getenv("HANK_NO_TMA"); c->no_tma = nt && nt[0] == '1'; }
   { const char* nt = getenv("HANK_NO_WIDE"); c->no_wide = nt && nt[0] == '1'; }
+  { const char* nt = getenv("HANK_NO_CLUSTER"); c->no_cluster = nt && nt[0] == '1'; }
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&c->ev0));
   CK(cudaEventCreate(&c->ev1));
@@ -300,7 +301,8 @@ int hank_ctx_create(hank_ctx** out, int device, int n_a, int n_e, int T, const d
   RC(dalloc(c, &tp.mbr, PG)); RC(dalloc(c, &tp.value_first, c->Gp));
   CK(cudaMemset(tp.pol, 0, PG * sizeof(double))); CK(cudaMemset(tp.bw, 0, bwb)); CK(cudaMemset(tp.fw, 0, fwb));
   CK(cudaMemset(tp.mbr, 0, PG * sizeof(int))); CK(cudaMemset(tp.value_first, 0, c->Gp * sizeof(double)));
-  RC(dalloc(c, &c->d_kdpart, (size_t)c->P * 16)); RC(dalloc(c, &c->d_KD, c->P));
+  RC(dalloc(c, &c->d_kdpart, (size_t)c->P * 16 * kMaxNE)); RC(dalloc(c, &c->d_KD, c->P));
+  RC(dalloc(c, &c->d_xch, (size_t)2 * c->Gp));
   RC(dalloc(c, &c->d_status, 4));
   CK(cudaMemset(c->d_status, 0, 4 * sizeof(int)));
   CK(cudaMallocHost((void**)&c->h_status, 4 * sizeof(int)));
@@ -318,7 +320,7 @@ void hank_ctx_destroy(hank_ctx* c) {
   dfree(tp.pol); dfree(tp.bw); dfree(tp.rho); dfree(tp.fw); dfree(tp.mbr);
   dfree(tp.value_first);
   dfree(c->d_dr); dfree(c->d_dw); dfree(c->d_dpol); dfree(c->d_dvalT); dfree(c->d_dvalue_first);
-  dfree(c->d_kdpart); dfree(c->d_KD); dfree(c->d_dkdpart); dfree(c->d_dKD); dfree(c->d_status);
+  dfree(c->d_xch); dfree(c->d_kdpart); dfree(c->d_KD); dfree(c->d_dkdpart); dfree(c->d_dKD); dfree(c->d_status);
   dfree(c->d_x); dfree(c->d_Z); dfree(c->d_F); dfree(c->d_V); dfree(c->d_JV);
   dfree(c->d_Jinv); dfree(c->d_newton); dfree(c->d_newton_i);
   for (auto& r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -406,6 +408,12 @@ static int backward_dev(hank_ctx* c, const double* r, const double* w, int K, co
 static int forward_dev(hank_ctx* c, const double* pol, int K, const double* dpol, double* KD, double* dKD) {
   if (!c->have_D0) return set_error(c, HANK_ERR_STATE, "hank_set_initial_dist has not been called");
   RC(sw_forward_primal(c, c->P, c->d_D0, pol, KD));
+  if (c->fp_cluster) {  // the cluster kernel leaves per-column, per-warp partials of <p_t, D_t>
+    Shape sh; pick_shape(c->n_a, &sh);
+    k_reduce_partials<<<nblk(c->P), 256, 0, c->stream>>>(c->d_kdpart, c->n_e * (sh.NT / 32), c->P, KD);
+    c->launches++;
+    CK(cudaGetLastError());
+  }
   c->have_forward = true;
   if (K > 0) {
     int nw = 16;

@@ -51,6 +51,9 @@ struct hank_ctx {
 
   // per-kernel CUDA-event timing of the sweep kernels (hank_profile / hank_kernel_times)
   bool profile = false;
+  bool no_cluster = false;       // HANK_NO_CLUSTER=1: single-CTA primal sweeps
+  bool fp_cluster = false;       // last forward primal ran on the cluster (per-column KD partials)
+  double* d_xch = nullptr;       // [2][NE][lda] cluster exchange buffer
   bool no_wide = false;          // HANK_NO_WIDE=1: never use the 256-thread / 6-lane tangent shape
   bool no_tma = false;           // HANK_NO_TMA=1: use the register-prefetch tangent kernels
   struct Rec { int kind; cudaEvent_t a, b; };

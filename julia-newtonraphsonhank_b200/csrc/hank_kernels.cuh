@@ -85,6 +85,13 @@ __device__ __forceinline__ double pow_v(double cg, double gamma) {
   if (G2) { double rx = 1.0 / cg; return rx * rx; }
   return pow(cg, -gamma);
 }
+// (cg^-γ, cg^(-γ-1)) with one division
+template <bool G2>
+__device__ __forceinline__ void pow_v2(double cg, double gamma, double& cgp, double& cgp1) {
+  const double rx = 1.0 / cg;
+  cgp = G2 ? rx * rx : pow(cg, -gamma);
+  cgp1 = cgp * rx;
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -100,6 +107,18 @@ __device__ __forceinline__ int lower_bound(const double* __restrict__ v, int n, 
     if (v[mid] < x) lo = mid + 1; else hi = mid;
   }
   return lo;
+}
+// Same result, branch-free with a fixed trip count (LDA >= n, power of two): independent searches
+// interleave instead of serialising on the data-dependent loop.
+template <int LDA>
+__device__ __forceinline__ int lower_bound_fixed(const double* __restrict__ v, int n, double x) {
+  int pos = 0;  // invariant: the first `pos` elements are < x
+#pragma unroll
+  for (int step = LDA; step >= 1; step >>= 1) {
+    const int np = pos + step;
+    if (np <= n && v[np - 1] < x) pos = np;
+  }
+  return pos;
 }
 
 // ======================================================================================
@@ -127,8 +146,10 @@ k_backward_primal(const Consts<NE> M, const Tape tp, const double* __restrict__ 
     for (int e = 0; e < NE; ++e) V[j][e] = a < n_a ? valueT[e * LDA + a] : 1.0;
   }
   __syncthreads();
+  double rn = rpath[P - 1], wn = wpath[P - 1];
   for (int t = P - 1; t >= 0; --t) {
-    const double r = rpath[t], w = wpath[t];
+    const double r = rn, w = wn;
+    if (t > 0) { rn = rpath[t - 1]; wn = wpath[t - 1]; }
     const double opr = 1.0 + r, rho = 1.0 / opr;
     double* polt = tp.pol + (size_t)t * NE * LDA + tid;
     if (tid == 0) tp.rho[t] = rho;
@@ -149,7 +170,7 @@ k_backward_primal(const Consts<NE> M, const Tape tp, const double* __restrict__ 
           const double S = (c - w * M.z[e]) + ga;
           ks[e * LDA + a] = rho * S;
           // ċ = Ḃ·yexp·B^(yexp-1);  k̇ = ρ·(ċ − ẇ z) + S·ρ̇,  ρ̇ = −(ρ/(1+r))·ṙ
-          bw_fields<LDA>(tp, NE, t, e)[BW_A1 * LDA + j * NT + tid] = rho * (M.beta * (M.yexp * (c / B)));
+          bw_fields<LDA>(tp, NE, t, e)[BW_A1 * LDA + j * NT + tid] = rho * (M.beta * (M.yexp * (G2 ? c * c * c : c / B)));
           bw_fields<LDA>(tp, NE, t, e)[BW_KR * LDA + j * NT + tid] = -(S * (rho / opr));
         }
       }
@@ -170,7 +191,7 @@ k_backward_primal(const Consts<NE> M, const Tape tp, const double* __restrict__ 
           if (x > kl) { i = n_a - 2; den = kl - k[i]; num = den; interior = false; }
           else if (x < k0) { i = 0; den = k[1] - k0; num = 0.0; interior = false; }
           else {
-            int lb = lower_bound(k, n_a, x);            // searchsortedfirst - 1 (0-based count)
+            int lb = lower_bound_fixed<LDA>(k, n_a, x);  // searchsortedfirst - 1 (0-based count)
             i = min(max(lb, 1), n_a - 1) - 1;           // find_knot_index clamp, left knot 0-based
             num = x - k[i]; den = k[i + 1] - k[i];
           }
@@ -181,16 +202,17 @@ k_backward_primal(const Consts<NE> M, const Tape tp, const double* __restrict__ 
           const double p = cons ? M.bc : q;
           const double cg = (opr * x + w * M.z[e]) - p;
           if (cg < 0.0 && !M.gamma_int) raise(status, 2, a, e, t);
-          const double cgp = pow_v<G2>(cg, M.gamma);
+          double cgp, cgp1;
+          pow_v2<G2>(cg, M.gamma, cgp, cgp1);
           polt[e * LDA + j * NT] = p;
           bw_idx<LDA>(tp, NE, t, e)[j * NT + tid] = i;
           // δ̇ = (1/den)(−k̇_i) + (−num/den²)(k̇_{i+1} − k̇_i);  q̇ = δ̇ (g_{i+1} − g_i)
           const bool live = interior && !cons;
-          const double dg = gi1 - gi, id = 1.0 / den, nd2 = num / (den * den);
+          const double dg = gi1 - gi, id = 1.0 / den, nd2 = delta * id;
           bw_fields<LDA>(tp, NE, t, e)[BW_CA * LDA + j * NT + tid] = live ? (nd2 - id) * dg : 0.0;
           bw_fields<LDA>(tp, NE, t, e)[BW_CB * LDA + j * NT + tid] = live ? -(nd2 * dg) : 0.0;
           // V̇ = ṙ·cg^-γ + (1+r)·(−γ)·cg^(−γ−1)·ċg,  ċg = ṙ a + ẇ z − ṗ
-          const double vf = opr * ((-M.gamma) * (cgp / cg));
+          const double vf = opr * ((-M.gamma) * cgp1);
           bw_fields<LDA>(tp, NE, t, e)[BW_VF * LDA + j * NT + tid] = vf;
           bw_fields<LDA>(tp, NE, t, e)[BW_E1 * LDA + j * NT + tid] = cgp + vf * x;
           V[j][e] = opr * cgp;
@@ -244,9 +266,24 @@ k_forward_primal(const Consts<NE> M, const Tape tp, const double* __restrict__ g
     for (int e = 0; e < NE; ++e) D[j][e] = a < n_a ? D0[e * LDA + a] : 0.0;
   }
   __syncthreads();
+  // the period's policies are requested one period ahead when they fit in registers
+  constexpr bool PRE = R * NE <= 14;
+  double pc[PRE ? R : 1][PRE ? NE : 1], pn[PRE ? R : 1][PRE ? NE : 1];
+  if (PRE) {
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+#pragma unroll
+      for (int e = 0; e < NE; ++e) pc[PRE ? j : 0][PRE ? e : 0] = tid + j * NT < n_a ? pol_in[e * LDA + j * NT + tid] : 0.0;
+  }
   for (int t = 0; t < P; ++t) {
     const double* polt = pol_in + (size_t)t * GP + tid;
     int* mbt = tp.mbr + (size_t)t * GP + tid;
+    if (PRE && t + 1 < P) {
+#pragma unroll
+      for (int j = 0; j < R; ++j)
+#pragma unroll
+        for (int e = 0; e < NE; ++e) pn[PRE ? j : 0][PRE ? e : 0] = tid + j * NT < n_a ? polt[GP + e * LDA + j * NT] : 0.0;
+    }
     double tmp[R][NE];
 #pragma unroll
     for (int e0 = 0; e0 < NE; e0 += CS) {
@@ -259,8 +296,8 @@ k_forward_primal(const Consts<NE> M, const Tape tp, const double* __restrict__ g
           for (int ee = 0; ee < CS; ++ee) {
             const int e = e0 + ee;
             if (e < NE) {
-              const double p = polt[e * LDA + j * NT];
-              const int m = lower_bound(g, n_a, p) + 1;  // Julia searchsortedfirst, 1-based
+              const double p = PRE ? pc[PRE ? j : 0][PRE ? e : 0] : polt[e * LDA + j * NT];
+              const int m = lower_bound_fixed<LDA>(g, n_a, p) + 1;  // Julia searchsortedfirst, 1-based
               double om, dco;
               if (m == 1) { om = 1.0; dco = 0.0; }
               else if (m > n_a) { om = 0.0; dco = 0.0; }  // all mass to node n_a via the (1-ω) leg
@@ -337,12 +374,18 @@ k_forward_primal(const Consts<NE> M, const Tape tp, const double* __restrict__ g
           for (int e = 0; e < NE; ++e) d += M.Pi[e][e2] * tmp[j][e];
           D[j][e2] = d;
           fw_fields<LDA>(tp, NE, t, e2)[FW_D * LDA + j * NT + tid] = d;
-          kacc += polt[e2 * LDA + j * NT] * d;
+          kacc += (PRE ? pc[PRE ? j : 0][PRE ? e2 : 0] : polt[e2 * LDA + j * NT]) * d;
         }
       }
     }
     kacc = warp_sum(kacc);
     if (lane == 0) kdpart[(size_t)t * NW + warp] = kacc;
+    if (PRE) {
+#pragma unroll
+      for (int j = 0; j < R; ++j)
+#pragma unroll
+        for (int e = 0; e < NE; ++e) pc[PRE ? j : 0][PRE ? e : 0] = pn[PRE ? j : 0][PRE ? e : 0];
+    }
   }
   __syncthreads();
   for (int t = tid; t < P; t += NT) {

@@ -7,6 +7,7 @@
 #include "hank_ctx.h"
 #include "hank_tangent.cuh"
 #include "hank_tangent_tma.cuh"
+#include "hank_primal_cluster.cuh"
 
 namespace hank {
 
@@ -43,10 +44,44 @@ static int set_smem(hank_ctx* c, KernelT k, size_t bytes) {
     return cuda_check(c, cudaGetLastError(), #kern);                                \
   } while (0)
 
+// Launch `kern` as ONE cluster of NE CTAs (one income state per CTA). Returns -1 if the cluster
+// cannot be scheduled (caller falls back to the single-CTA kernel).
+template <int NE, typename KernelT, typename... Args>
+static int launch_cluster(hank_ctx* c, int kind, KernelT kern, int block, size_t smem, const char* name, Args... args) {
+  if (NE > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  int rc = set_smem(c, kern, smem);
+  if (rc) return rc;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(NE); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = NE; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int ncl = 0;
+  if (cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg) != cudaSuccess || ncl < 1) { cudaGetLastError(); return -1; }
+  cudaEvent_t ev = prof_begin(c);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args...);
+  prof_end(c, kind, ev);
+  c->launches++;
+  return cuda_check(c, e, name);
+}
+
 // ---- backward primal -------------------------------------------------------------------
 template <int NE, int R, int NT>
 static int bp_launch(hank_ctx* c, int P, const double* valueT, const double* r, const double* w) {
   const Consts<NE> M = make_consts<NE>(c, P);
+  if (!c->no_cluster && NE > 1) {
+    const size_t smem_c = (size_t)2 * NT * R * sizeof(double);
+    int rc = c->gamma == 2.0
+        ? launch_cluster<NE>(c, KIND_BP, k_backward_primal_cl<NE, R, NT, true>, NT, smem_c, "k_backward_primal_cl", M, c->tape,
+                             (const double*)c->d_grid, valueT, r, w, c->d_xch, c->d_status)
+        : launch_cluster<NE>(c, KIND_BP, k_backward_primal_cl<NE, R, NT, false>, NT, smem_c, "k_backward_primal_cl", M, c->tape,
+                             (const double*)c->d_grid, valueT, r, w, c->d_xch, c->d_status);
+    if (rc >= 0) return rc;
+  }
   const size_t smem = ((size_t)NE * NT * R + NT * R) * sizeof(double);
   if (c->gamma == 2.0)
     HANK_LAUNCH(KIND_BP, (k_backward_primal<NE, R, NT, true>), 1, NT, smem, M, c->tape, c->d_grid, valueT, r, w, c->d_status);
@@ -68,7 +103,15 @@ template <int NE, int R, int NT, int CS>
 static int fp_launch(hank_ctx* c, int P, const double* D0, const double* pol, double* KD) {
   const Consts<NE> M = make_consts<NE>(c, P);
   constexpr int LDA = NT * R;
+  if (!c->no_cluster && NE > 1 && CS == NE) {   // (the CS < NE instantiation only exists as the single-CTA fallback)
+    const size_t smem_c = (size_t)3 * LDA * sizeof(double) + ((size_t)LDA + LDA + 4) * sizeof(int);
+    int rc = launch_cluster<NE>(c, KIND_FP, k_forward_primal_cl<NE, R, NT>, NT, smem_c, "k_forward_primal_cl", M, c->tape,
+                                (const double*)c->d_grid, D0, pol, c->d_xch, c->d_kdpart, c->d_status);
+    if (rc >= 0) { c->fp_cluster = true; return rc; }
+  }
+  c->fp_cluster = false;
   const size_t smem = ((size_t)2 * CS * LDA + LDA) * sizeof(double) + ((size_t)CS * LDA + (size_t)CS * (LDA + 4)) * sizeof(int);
+  if (smem > (size_t)c->smem_max) return -2;  // caller retries with fewer columns staged at once
   HANK_LAUNCH(KIND_FP, (k_forward_primal<NE, R, NT, CS>), 1, NT, smem, M, c->tape, c->d_grid, D0, pol, c->d_kdpart, KD, c->d_status);
 }
 template <int NE>
@@ -79,9 +122,9 @@ int Sweeps<NE>::forward_primal(hank_ctx* c, int P, const double* D0, const doubl
   if (!pick_shape(c->n_a, &s)) return set_error(c, 1, "n_a > 2048 is not supported");
   const size_t lda = c->lda;
   const size_t full = ((size_t)2 * NE * lda + lda) * 8 + ((size_t)NE * lda + (size_t)NE * (lda + 4)) * 4;
-  const bool fits = full <= (size_t)c->smem_max;
+  const bool fits = full <= (size_t)c->smem_max || !c->no_cluster;
   constexpr int C4 = small_cs<NE>();
-#define FP(R_, NT_) do { if (fits) return fp_launch<NE, R_, NT_, NE>(c, P, D0, pol, KD); \
+#define FP(R_, NT_) do { if (fits) { int rc_ = fp_launch<NE, R_, NT_, NE>(c, P, D0, pol, KD); if (rc_ != -2) return rc_; } \
                          return fp_launch<NE, R_, NT_, C4>(c, P, D0, pol, KD); } while (0)
   if (s.NT == 256) FP(1, 256);
   if (s.R == 1) FP(1, 512);
