@@ -139,7 +139,9 @@ int hank_ks_jacobian_columns_dev(hank_ctx* ctx, int col_begin, int col_end, doub
 /* NewtonRaphsonHANK / y_Iteration (NewtonRaphson.jl:27-114) with the sweeps, the residuals and
  * the preconditioner solve on the device.  Jbar: n x n column-major (the steady-state Jacobian
  * matrix, NewtonRaphson.jl:97).  solver: 0 = restarted GMRES(20) with IterativeSolvers 0.9.4
- * defaults (reference-faithful), 1 = LU factorisation of Jbar (exact preconditioner solve).
+ * defaults (reference-faithful), 1 = LU factorisation of Jbar (exact preconditioner solve),
+ * 2 = as 1 with J(x) assembled once per outer iteration from batched unit-seed lanes, so the
+ * inner J(x)*y products are GEMVs (same quantity as JVP(fullFunction, x, y)).
  * stats[0..4] = outer iterations, JVPs, F evaluations, final ||y||, GMRES iterations;
  * inner_counts (may be NULL) receives up to 100 inner-iteration counts.                      */
 int hank_newton_solve(hank_ctx* ctx, const double* Jbar, const double* x0, const double* Z,

@@ -11,6 +11,10 @@
 //             and is skipped.
 //   solver 1: J̅⁻¹ formed once by cuSOLVER LU (getrf/getrs on the identity), then one FP64 GEMV
 //             per inner iteration.
+//   solver 2: as 1, and J(x) itself is assembled once per outer iteration from batched unit-seed
+//             tangent lanes (hank_ks_jacobian_columns_dev, all SMs busy) so that the ~40 inner
+//             products J(x)·y become GEMVs instead of 40 strictly sequential single-lane sweeps.
+//             Same quantity (JVP(fullFunction, x, y) = J(x)·y), different summation order.
 #include <cmath>
 #include <cstdio>
 #include <limits>
@@ -62,6 +66,15 @@ __global__ void k_gemv_partial(const double* __restrict__ A, const double* __res
   double acc = 0.0;
   for (int j = j0; j < j1; ++j) acc = fma(A[(size_t)j * n + i], __ldg(v + j), acc);
   part[(size_t)s * n + i] = acc;
+}
+// out = a − Σ_s part[s]   (rhs = F(x) − J(x)·y from the split GEMV)
+__global__ void k_sub_partial(const double* a, const double* __restrict__ part, int n, double* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    double s = 0.0;
+    for (int k = 0; k < kSplit; ++k) s += part[(size_t)k * n + i];
+    out[i] = a[i] - s;
+  }
 }
 __global__ void k_sub(const double* a, const double* b, int n, double* out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -282,7 +295,9 @@ extern "C" int hank_newton_solve(hank_ctx* c, const double* Jbar, const double* 
   if (!c || !Jbar || !x0 || !Z || !x_out) return HANK_ERR_ARG;
   CK(cudaSetDevice(c->device));
   if (!c->ks_ready) return set_error(c, HANK_ERR_STATE, "hank_ks_configure has not been called");
-  if (solver != 0 && solver != 1) return set_error(c, HANK_ERR_ARG, "solver must be 0 (gmres) or 1 (lu)");
+  if (solver < 0 || solver > 2) return set_error(c, HANK_ERR_ARG, "solver must be 0 (gmres), 1 (lu) or 2 (lu, batched J(x))");
+  const bool batched = solver == 2;
+  if (batched) solver = 1;
   const int P = c->P, n = 4 * P;
   const size_t nn = (size_t)n * n;
   // workspace
@@ -292,6 +307,8 @@ extern "C" int hank_newton_solve(hank_ctx* c, const double* Jbar, const double* 
   if (c->d_Jinv) { cudaFree(c->d_Jinv); c->d_Jinv = nullptr; }
   CK(cudaMalloc((void**)&c->d_newton, (nvec * n + extra) * sizeof(double)));
   CK(cudaMalloc((void**)&c->d_Jinv, nn * sizeof(double) * (solver == 1 ? 2 : 1)));
+  double* Jx = nullptr;  // J(x), column-major, for the batched mode (reuses the LU scratch half)
+  if (batched) Jx = c->d_Jinv + nn;
   NewtonBufs B;
   double* p = c->d_newton;
   B.x = p; p += n; B.y = p; p += n; B.yold = p; p += n; B.Fx = p; p += n; B.Lxy = p; p += n; B.rhs = p; p += n;
@@ -350,6 +367,7 @@ extern "C" int hank_newton_solve(hank_ctx* c, const double* Jbar, const double* 
   while (eps < ynorm && outer < 100) {
     RC(hank_ks_linearize_dev(c, B.x, c->d_Z, B.Fx));
     ++fevals;
+    if (batched) RC(hank_ks_jacobian_columns_dev(c, 1, n + 1, Jx));
     k_fill<<<nb, 256, 0, c->stream>>>(B.yold, n, 1.0);
     k_fill<<<nb, 256, 0, c->stream>>>(B.R, n, 1.0);
     k_norms<<<1, 1024, 0, c->stream>>>(B.y, B.yold, n, B.scal);
@@ -358,9 +376,14 @@ extern "C" int hank_newton_solve(hank_ctx* c, const double* Jbar, const double* 
     double diff = h_scal[0];
     int inner = 0;
     while (eps_inner < diff) {
-      RC(hank_ks_jvp_dev(c, 1, B.y, B.Lxy));
+      if (batched) {
+        RC(gemv_partial(c, Jx, B.y, n, B.part));
+        k_sub_partial<<<nb, 256, 0, c->stream>>>(B.Fx, B.part, n, B.rhs);
+      } else {
+        RC(hank_ks_jvp_dev(c, 1, B.y, B.Lxy));
+        k_sub<<<nb, 256, 0, c->stream>>>(B.Fx, B.Lxy, n, B.rhs);
+      }
       ++jvps; ++inner;
-      k_sub<<<nb, 256, 0, c->stream>>>(B.Fx, B.Lxy, n, B.rhs);
       c->launches++;
       if (solver == 1) {
         RC(gemv_partial(c, B.J, B.rhs, n, B.part));

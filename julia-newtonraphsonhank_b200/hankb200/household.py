@@ -228,7 +228,7 @@ class HouseholdBlock:
         x0 = _f(x0, (n,)); Z = _f(Z, (self.P,))
         xo = np.empty(n); stats = np.zeros(8); inner = np.zeros(100, dtype=np.int32)
         rc = self._L.hank_newton_solve(self._h, _p(Jcm), _p(x0), _p(Z), float(eps), float(eps_inner),
-                                       {"gmres": 0, "lu": 1}[solver], _p(xo), _p(stats), inner.ctypes.data_as(c_ip))
+                                       {"gmres": 0, "lu": 1, "lu_batched": 2}[solver], _p(xo), _p(stats), inner.ctypes.data_as(c_ip))
         self._ck(rc)
         outer = int(stats[0])
         return xo, dict(outer=outer, jvps=int(stats[1]), fevals=int(stats[2]), ynorm=float(stats[3]),

@@ -68,6 +68,10 @@ def test_golden_ks_gpu(path):
     x, st = blk.newton_solve(g["Jbar"], g["x0"], g["Z"], solver="lu")
     assert st["inner"] == list(g["newton_inner"]), (st, list(g["newton_inner"]))
     assert close(x, g["x_newton"]), maxerr(x, g["x_newton"])
+    # batched mode: J(x) assembled once per outer iteration from unit-seed lanes, inner J(x)y by GEMV
+    xb, sb = blk.newton_solve(g["Jbar"], g["x0"], g["Z"], solver="lu_batched")
+    assert sb["inner"] == st["inner"], (sb, st)
+    assert close(xb, x), maxerr(xb, x)
     blk.close()
 
 
