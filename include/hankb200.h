@@ -84,6 +84,12 @@ int hank_egm_step(hank_ctx* ctx, const double* value_next, const double* dvalue_
                   double w, int K, const double* dr, const double* dw, double* value,
                   double* policy, double* dvalue, double* dpolicy);
 
+/* Inner VFI of get_xVals (SteadyState.jl:132-141): iterate the EGM step from a matrix of ones until
+ * max|dValue| < eps on the primal values (at most max_iter steps), carrying K lanes.  Outputs as
+ * hank_egm_step: the converged Value and the policy of the last step; *iters = steps after the first. */
+int hank_vfi(hank_ctx* ctx, double r, double w, int K, const double* dr, const double* dw, double eps,
+             int max_iter, double* value, double* policy, double* dvalue, double* dpolicy, int* iters);
+
 /* ---- sweeps -------------------------------------------------------------------------- */
 /* BackwardIteration(xVec_endog, exog_paths, model, ss_end) — BackwardIteration.jl:46-116.
  * Only r and w enter the KS household block (KrusellSmith.jl:53-54), so the sweep takes their

@@ -223,6 +223,19 @@ static int ensure_V(hank_ctx* c, int K) {
 
 static inline int nblk(size_t n, int b = 256) { return (int)((n + b - 1) / b); }
 
+// scratch of the single-step entry points: incoming value + K lanes, outgoing K lanes
+static int ensure_egm(hank_ctx* c, int K) {
+  if (K <= c->egm_cap) return HANK_OK;
+  dfree(c->d_dvalT); dfree(c->d_dvalue_first);
+  c->egm_cap = -1;
+  RC(dalloc(c, &c->d_dvalT, (size_t)(K + 1) * c->Gp));
+  RC(dalloc(c, &c->d_dvalue_first, (size_t)std::max(K, 1) * c->Gp));
+  CK(cudaMemsetAsync(c->d_dvalT, 0, (size_t)(K + 1) * c->Gp * sizeof(double), c->stream));
+  CK(cudaMemsetAsync(c->d_dvalue_first, 0, (size_t)std::max(K, 1) * c->Gp * sizeof(double), c->stream));
+  c->egm_cap = K;
+  return HANK_OK;
+}
+
 // Copies `rows` columns of n_a doubles between the caller's dense [rows][n_a] layout and the
 // device's padded [rows][lda] layout.
 static int copy_in(hank_ctx* c, double* dst_padded, const double* src_dense, size_t rows) {
@@ -486,11 +499,8 @@ int hank_egm_step(hank_ctx* c, const double* value_next, const double* dvalue_ne
   if (K > 0) RC(ensure_lanes(c, K));
   if (K > c->Kcap && K > 0) return set_error(c, HANK_ERR_ARG, "K exceeds device memory");
   // scratch for the incoming value and its lanes
-  static thread_local int dummy = 0; (void)dummy;
-  dfree(c->d_dvalT); dfree(c->d_dvalue_first);
   const int Gp = c->Gp;
-  RC(dalloc(c, &c->d_dvalT, (size_t)(K + 1) * Gp));
-  RC(dalloc(c, &c->d_dvalue_first, (size_t)std::max(K, 1) * Gp));
+  RC(ensure_egm(c, K));
   double* d_vn = c->d_dvalT + (size_t)K * Gp;
   RC(copy_in(c, d_vn, value_next, c->n_e));
   CK(cudaMemcpyAsync(c->d_r, &r, sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -509,6 +519,79 @@ int hank_egm_step(hank_ctx* c, const double* value_next, const double* dvalue_ne
   if (K > 0) {
     RC(copy_out(c, dvalue, c->d_dvalue_first, (size_t)K * c->n_e));
     for (int l = 0; l < K; ++l)  // device [1][n_e][K][lda] -> caller [K][n_e][n_a]
+      CK(cudaMemcpy2DAsync(dpolicy + (size_t)l * c->G, (size_t)c->n_a * 8, c->d_dpol + (size_t)l * c->lda,
+                           (size_t)K * c->lda * 8, (size_t)c->n_a * 8, c->n_e, cudaMemcpyDefault, c->stream));
+  }
+  return check_status(c);
+}
+
+// Inner VFI of get_xVals (SteadyState.jl:132-141): iterate value_fn from a matrix of ones until
+// max|ΔValue| < eps on the primal values, carrying K tangent lanes, entirely on the device (one
+// 8-byte read-back per step for the stopping rule).
+__global__ void k_fill_d(double* a, size_t n, double v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = v;
+}
+__global__ void k_max_abs_diff(const double* __restrict__ a, const double* __restrict__ b, int n_e, int lda, int n_a,
+                               double* out) {
+  __shared__ double red[32];
+  double m = 0.0;
+  for (int i = threadIdx.x; i < n_e * lda; i += blockDim.x)
+    if (i % lda < n_a) m = fmax(m, fabs(a[i] - b[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
+    *out = m;
+  }
+}
+
+int hank_vfi(hank_ctx* c, double r, double w, int K, const double* dr, const double* dw, double eps, int max_iter,
+             double* value, double* policy, double* dvalue, double* dpolicy, int* iters) {
+  CK(cudaSetDevice(c->device));
+  if (K < 0 || (K > 0 && (!dr || !dw))) return set_error(c, HANK_ERR_ARG, "K > 0 needs dr and dw");
+  if (K > 0) RC(ensure_lanes(c, K));
+  if (K > c->Kcap && K > 0) return set_error(c, HANK_ERR_ARG, "K exceeds device memory");
+  const int Gp = c->Gp;
+  RC(ensure_egm(c, K));
+  double* d_v = c->d_dvalT + (size_t)K * Gp;  // current value; lanes at d_dvalT[0..K)
+  double* d_tol = c->d_KD;                     // 8-byte scratch
+  CK(cudaMemcpyAsync(c->d_r, &r, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_w, &w, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (K > 0) {
+    CK(cudaMemcpyAsync(c->d_dr, dr, K * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_dw, dw, K * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(c->d_dvalT, 0, (size_t)K * Gp * sizeof(double), c->stream));
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  k_fill_d<<<nblk(Gp), 256, 0, c->stream>>>(d_v, (size_t)Gp, 1.0);
+  c->launches++;
+  c->have_backward = false; c->have_forward = false; c->linearized = false; c->K_last = K;
+  auto step = [&]() -> int {
+    RC(sw_backward_primal(c, 1, d_v, c->d_r, c->d_w));
+    if (K > 0) RC(sw_backward_tangent(c, 1, K, c->d_dr, c->d_dw, c->d_dvalT, c->d_dpol, c->d_dvalue_first));
+    return HANK_OK;
+  };
+  RC(step());
+  int it = 0;
+  for (; it < max_iter; ++it) {
+    k_max_abs_diff<<<1, 1024, 0, c->stream>>>(c->tape.value_first, d_v, c->n_e, c->lda, c->n_a, d_tol);
+    c->launches++;
+    CK(cudaMemcpyAsync(d_v, c->tape.value_first, (size_t)Gp * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    if (K > 0) CK(cudaMemcpyAsync(c->d_dvalT, c->d_dvalue_first, (size_t)K * Gp * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    double tol = 0.0;
+    CK(cudaMemcpyAsync(&tol, d_tol, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    RC(check_status(c));
+    if (!(tol >= eps)) break;  // tol < eps, or NaN: stop like the reference's comparison would not
+    RC(step());
+  }
+  if (iters) *iters = it;
+  RC(copy_out(c, value, (const double*)c->tape.value_first, c->n_e));
+  RC(copy_out(c, policy, (const double*)c->tape.pol, c->n_e));
+  if (K > 0) {
+    RC(copy_out(c, dvalue, (const double*)c->d_dvalue_first, (size_t)K * c->n_e));
+    for (int l = 0; l < K; ++l)
       CK(cudaMemcpy2DAsync(dpolicy + (size_t)l * c->G, (size_t)c->n_a * 8, c->d_dpol + (size_t)l * c->lda,
                            (size_t)K * c->lda * 8, (size_t)c->n_a * 8, c->n_e, cudaMemcpyDefault, c->stream));
   }

@@ -25,7 +25,8 @@ struct hank_ctx {
   // tangent lanes
   int Kcap = 0, K_last = 0;
   double *d_dr = nullptr, *d_dw = nullptr, *d_dpol = nullptr;
-  double *d_dvalT = nullptr, *d_dvalue_first = nullptr;  // egm_step lanes
+  double *d_dvalT = nullptr, *d_dvalue_first = nullptr;  // egm_step / vfi lanes
+  int egm_cap = -1;              // lanes the egm scratch is sized for
   double *d_kdpart = nullptr, *d_KD = nullptr, *d_dkdpart = nullptr, *d_dKD = nullptr;
   int* d_status = nullptr;
   int* h_status = nullptr;  // pinned

@@ -32,6 +32,7 @@ SIGNATURES = {
     "hank_set_terminal": (C.c_int, [ctx_p, c_dp]),
     "hank_set_initial_dist": (C.c_int, [ctx_p, c_dp]),
     "hank_egm_step": (C.c_int, [ctx_p, c_dp, c_dp, C.c_double, C.c_double, C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    "hank_vfi": (C.c_int, [ctx_p, C.c_double, C.c_double, C.c_int, c_dp, c_dp, C.c_double, C.c_int, c_dp, c_dp, c_dp, c_dp, c_ip]),
     "hank_backward": (C.c_int, [ctx_p, c_dp, c_dp, C.c_int, c_dp, c_dp]),
     "hank_forward": (C.c_int, [ctx_p, c_dp, c_dp]),
     "hank_forward_policies": (C.c_int, [ctx_p, c_dp, C.c_int, c_dp, c_dp, c_dp]),

@@ -122,6 +122,19 @@ class HouseholdBlock:
                                        _p(value), _p(policy), _p(dvalue), _p(dpolicy)))
         return value, policy, dvalue, dpolicy
 
+    def vfi(self, r, w, dr=None, dw=None, eps=1e-6, max_iter=10_000):
+        """Inner VFI of get_xVals (SteadyState.jl:132-141) on the device: returns
+        (Value, KD, dValue, dKD, steps)."""
+        ne, na = self.n_e, self.n_a
+        K = 0 if dr is None else len(dr)
+        drr = None if K == 0 else _f(dr, (K,)); dww = None if K == 0 else _f(dw, (K,))
+        value = np.empty((ne, na)); policy = np.empty((ne, na))
+        dvalue = np.empty((K, ne, na)); dpolicy = np.empty((K, ne, na))
+        it = C.c_int(0)
+        self._ck(self._L.hank_vfi(self._h, float(r), float(w), K, _p(drr), _p(dww), float(eps), int(max_iter),
+                                  _p(value), _p(policy), _p(dvalue), _p(dpolicy), C.byref(it)))
+        return value, policy, dvalue, dpolicy, it.value
+
     # -- sweeps -----------------------------------------------------------------------------
     def backward(self, r, w, dr=None, dw=None):
         """BackwardIteration: policies (and K tangent lanes) stay on the device."""

@@ -56,3 +56,25 @@ def make_oracle(m, T):
 def make_block(m, T, device=0):
     from hankb200.household import HouseholdBlock
     return HouseholdBlock(m["grid"], m["z"], m["Pi"], m["beta"], m["gamma"], m["borrow_cons"], T, device=device)
+
+
+def ks_yaml_dict(n_a=200, n_e=7, T=150):
+    """The reference's model-file contract (schema and values of KrusellSmith.yaml:12-116), built as a dict so the
+    tests can write it to a temporary YAML file for build_model_from_yaml."""
+    P = lambda name, value: {"name": name, "value": value}
+    return {
+        "file": {"name": "Krusell Smith Model", "function_file": "KrusellSmith.jl"},
+        "parameters": {"model": [P("β", 0.98), P("borrow_cons", 0.0), P("γ", 2.0), P("α", 0.36), P("δ", 0.08)],
+                       "computational": [P("T", T), P("ε", 1.0e-6), P("dx", 0.001)]},
+        "dimensions": [
+            {"name": "wealth", "type": "endogenous", "policy_var": "KD", "grid_function": "double_exponential",
+             "params": {"n": n_a, "grid_min": 0.0, "grid_max": 200.0}},
+            {"name": "productivity", "type": "exogenous", "grid_function": "rouwenhorst_discretization",
+             "params": {"n": n_e, "ρ": 0.966, "σ": 0.283}}],
+        "variables": {"endogenous": [{"name": k} for k in ("Y", "KS", "r", "w")],
+                      "exogenous": [{"name": "Z", "seq_function": "exogenousZ"}],
+                      "heterogeneous": [{"name": "KD"}, {"function": "ValueFunction"}]},
+        "equations": ["Y = Z * KS(-1)^α", "r + δ = α * Z * KS(-1)^(α-1)", "w = (1-α) * Z * KS(-1)^α", "KS = KD"],
+        "steady_states": {"initial": {"fixed": {"Z": 1.0}, "guesses": {"r": 0.04, "w": 1.0, "Y": 1.5, "KS": 3.5}},
+                          "ending": {"fixed": {"Z": 2.0}, "guesses": {"r": 0.04, "w": 1.5, "Y": 2.0, "KS": 5.0}}},
+    }
