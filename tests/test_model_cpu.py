@@ -16,7 +16,7 @@ def test_build_model_from_yaml(tmp_path):
     assert mod.var_names == ("Y", "KS", "r", "w", "KD", "Z")
     w, pr = mod.heterogeneity["wealth"], mod.heterogeneity["productivity"]
     assert w.n == 200 and pr.n == 7 and w.policy_var == "KD"
-    assert np.allclose(w.grid, O.double_exponential(200, 0.0, 200.0), rtol=4e-16, atol=1e-17)
+    assert np.allclose(w.grid, O.double_exponential(200, 0.0, 200.0), rtol=1e-14, atol=1e-16)
     zo, Pio, _ = O.rouwenhorst(7, 0.966, 0.283)
     assert np.allclose(pr.grid, zo, rtol=1e-15) and np.allclose(pr.transition, Pio, rtol=1e-15, atol=1e-18)
     assert mod.ss_initial["fixed"]["Z"] == 1.0 and mod.ss_ending["fixed"]["Z"] == 2.0
