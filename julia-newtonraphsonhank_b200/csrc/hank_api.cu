@@ -164,6 +164,12 @@ static int sw_forward_primal(hank_ctx* c, int P, const double* D0, const double*
 static int sw_forward_tangent(hank_ctx* c, int P, int K, const double* dpol, double* dkdpart, int* nw) {
   NE_DISPATCH(c, forward_tangent(c, P, K, dpol, dkdpart, nw));
 }
+static int sw_lanes_per_cta(hank_ctx* c, int K) { NE_DISPATCH(c, lanes_per_cta(c, K)); }
+// lane stride of the policy-tangent array for a K-lane pass: K rounded up to the lanes per CTA
+static int lane_stride(hank_ctx* c, int K) {
+  const int L = std::max(1, sw_lanes_per_cta(c, K));
+  return (K + L - 1) / L * L;
+}
 static inline size_t bw_chunk(const hank_ctx* c) { return (size_t)52 * c->lda; }
 static inline size_t fw_chunk(const hank_ctx* c) { return (size_t)FW_NF * 8 * c->lda + (size_t)4 * (c->lda + 4); }
 
@@ -196,15 +202,15 @@ static int ensure_lanes(hank_ctx* c, int K) {
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   const size_t have = (size_t)c->Kcap * per_lane;
-  int Kmax = (int)std::min<size_t>((size_t)K, (size_t)(0.85 * (double)(free_b + have)) / per_lane);
+  int Kmax = (int)std::min<size_t>((size_t)K, (size_t)(0.85 * (double)(free_b + have)) / per_lane - 8);
   if (Kmax < 1) return set_error(c, HANK_ERR_CUDA, "not enough device memory for one tangent lane");
   if (Kmax <= c->Kcap) return HANK_OK;
   dfree(c->d_dr); dfree(c->d_dw); dfree(c->d_dpol); dfree(c->d_dkdpart); dfree(c->d_dKD);
   c->Kcap = 0;
   RC(dalloc(c, &c->d_dr, (size_t)Kmax * c->P_alloc));
   RC(dalloc(c, &c->d_dw, (size_t)Kmax * c->P_alloc));
-  RC(dalloc(c, &c->d_dpol, (size_t)Kmax * c->P_alloc * c->Gp));
-  CK(cudaMemsetAsync(c->d_dpol, 0, (size_t)Kmax * c->P_alloc * c->Gp * sizeof(double), c->stream));
+  RC(dalloc(c, &c->d_dpol, (size_t)(Kmax + 8) * c->P_alloc * c->Gp));
+  CK(cudaMemsetAsync(c->d_dpol, 0, (size_t)(Kmax + 8) * c->P_alloc * c->Gp * sizeof(double), c->stream));
   RC(dalloc(c, &c->d_dkdpart, (size_t)Kmax * c->P_alloc * 16));
   RC(dalloc(c, &c->d_dKD, (size_t)Kmax * c->P_alloc));
   c->Kcap = Kmax;
@@ -333,9 +339,9 @@ void hank_ctx_destroy(hank_ctx* c) {
   dfree(tp.pol); dfree(tp.bw); dfree(tp.rho); dfree(tp.fw); dfree(tp.mbr);
   dfree(tp.value_first);
   dfree(c->d_dr); dfree(c->d_dw); dfree(c->d_dpol); dfree(c->d_dvalT); dfree(c->d_dvalue_first);
-  dfree(c->d_xch); dfree(c->d_kdpart); dfree(c->d_KD); dfree(c->d_dkdpart); dfree(c->d_dKD); dfree(c->d_status);
+  dfree(c->d_jac_idx); dfree(c->d_xch); dfree(c->d_kdpart); dfree(c->d_KD); dfree(c->d_dkdpart); dfree(c->d_dKD); dfree(c->d_status);
   dfree(c->d_x); dfree(c->d_Z); dfree(c->d_F); dfree(c->d_V); dfree(c->d_JV);
-  dfree(c->d_Jinv); dfree(c->d_newton); dfree(c->d_newton_i);
+  dfree(c->d_Jinv); dfree(c->d_newton); dfree(c->d_newton_i); dfree(c->d_lu_work);
   for (auto& r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   if (c->h_status) cudaFreeHost(c->h_status);
@@ -476,8 +482,9 @@ int hank_forward_policies(hank_ctx* c, const double* policy, int K, const double
   const int P = c->P;
   if (K > 0) { RC(ensure_lanes(c, K)); if (K > c->Kcap) return set_error(c, HANK_ERR_ARG, "K exceeds device memory"); }
   RC(copy_in(c, c->tape.pol, policy, (size_t)P * c->n_e));
-  for (int l = 0; l < K; ++l)  // caller [K][P][n_e][n_a] -> device [P][n_e][K][lda]
-    CK(cudaMemcpy2DAsync(c->d_dpol + (size_t)l * c->lda, (size_t)K * c->lda * 8, dpolicy + (size_t)l * P * c->G,
+  const size_t Kpf = K > 0 ? (size_t)lane_stride(c, K) : 0;
+  for (int l = 0; l < K; ++l)  // caller [K][P][n_e][n_a] -> device [P][n_e][Kp][lda]
+    CK(cudaMemcpy2DAsync(c->d_dpol + (size_t)l * c->lda, Kpf * c->lda * 8, dpolicy + (size_t)l * P * c->G,
                          (size_t)c->n_a * 8, (size_t)c->n_a * 8, (size_t)P * c->n_e, cudaMemcpyDefault, c->stream));
   c->have_backward = false; c->linearized = false; c->K_last = K;
   RC(forward_dev(c, c->tape.pol, K, c->d_dpol, c->d_KD, c->d_dKD));
@@ -520,7 +527,7 @@ int hank_egm_step(hank_ctx* c, const double* value_next, const double* dvalue_ne
     RC(copy_out(c, dvalue, c->d_dvalue_first, (size_t)K * c->n_e));
     for (int l = 0; l < K; ++l)  // device [1][n_e][K][lda] -> caller [K][n_e][n_a]
       CK(cudaMemcpy2DAsync(dpolicy + (size_t)l * c->G, (size_t)c->n_a * 8, c->d_dpol + (size_t)l * c->lda,
-                           (size_t)K * c->lda * 8, (size_t)c->n_a * 8, c->n_e, cudaMemcpyDefault, c->stream));
+                           (size_t)lane_stride(c, K) * c->lda * 8, (size_t)c->n_a * 8, c->n_e, cudaMemcpyDefault, c->stream));
   }
   return check_status(c);
 }
@@ -593,7 +600,7 @@ int hank_vfi(hank_ctx* c, double r, double w, int K, const double* dr, const dou
     RC(copy_out(c, dvalue, (const double*)c->d_dvalue_first, (size_t)K * c->n_e));
     for (int l = 0; l < K; ++l)
       CK(cudaMemcpy2DAsync(dpolicy + (size_t)l * c->G, (size_t)c->n_a * 8, c->d_dpol + (size_t)l * c->lda,
-                           (size_t)K * c->lda * 8, (size_t)c->n_a * 8, c->n_e, cudaMemcpyDefault, c->stream));
+                           (size_t)lane_stride(c, K) * c->lda * 8, (size_t)c->n_a * 8, c->n_e, cudaMemcpyDefault, c->stream));
   }
   return check_status(c);
 }
@@ -604,8 +611,11 @@ int hank_get_policy(hank_ctx* c, int t, int lane, double* out) {
   if (t < 1 || t > c->P || lane < 0 || lane > c->K_last) return set_error(c, HANK_ERR_ARG, "t or lane out of range");
   if (lane == 0) RC(copy_out(c, out, (const double*)(c->tape.pol + (size_t)(t - 1) * c->Gp), c->n_e));
   else  // tangents are [t][e][K][lda]
-    CK(cudaMemcpy2DAsync(out, (size_t)c->n_a * 8, c->d_dpol + ((size_t)(t - 1) * c->n_e * c->K_last + (lane - 1)) * c->lda,
-                         (size_t)c->K_last * c->lda * 8, (size_t)c->n_a * 8, c->n_e, cudaMemcpyDefault, c->stream));
+  {
+    const size_t Kp = (size_t)lane_stride(c, c->K_last);
+    CK(cudaMemcpy2DAsync(out, (size_t)c->n_a * 8, c->d_dpol + ((size_t)(t - 1) * c->n_e * Kp + (lane - 1)) * c->lda,
+                         Kp * c->lda * 8, (size_t)c->n_a * 8, c->n_e, cudaMemcpyDefault, c->stream));
+  }
   CK(cudaStreamSynchronize(c->stream));
   return HANK_OK;
 }
@@ -729,8 +739,13 @@ int hank_ks_jacobian_columns_dev(hank_ctx* c, int col_begin, int col_end, double
     if (((c0 + j) & 3) >= 2) lane_col.push_back(c0 + j);
   int Kh = (int)lane_col.size();
   if (Kh > 0) RC(ensure_lanes(c, Kh));
-  int* d_lane_col = nullptr; int* d_col_lane = nullptr;
-  RC(dalloc(c, &d_lane_col, std::max(Kh, 1))); RC(dalloc(c, &d_col_lane, ncols));
+  if (c->jac_idx_cap < ncols) {
+    dfree(c->d_jac_idx);
+    c->jac_idx_cap = 0;
+    RC(dalloc(c, &c->d_jac_idx, (size_t)2 * ncols));
+    c->jac_idx_cap = ncols;
+  }
+  int* d_lane_col = c->d_jac_idx; int* d_col_lane = c->d_jac_idx + c->jac_idx_cap;
   const int chunk = Kh > 0 ? c->Kcap : 1;
   // Y / KS columns first need no sweeps: handled by col_lane = -1. Household lanes go in chunks of
   // Kcap; each chunk writes the columns it owns.
@@ -759,7 +774,6 @@ int hank_ks_jacobian_columns_dev(hank_ctx* c, int col_begin, int col_end, double
     CK(cudaStreamSynchronize(c->stream));  // host vectors are reused by the next chunk
     done_cols = col_hi;
   }
-  cudaFree(d_lane_col); cudaFree(d_col_lane);
   return HANK_OK;
 }
 

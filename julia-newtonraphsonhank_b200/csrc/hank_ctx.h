@@ -40,8 +40,9 @@ struct hank_ctx {
 
   // dense solve (Newton)
   void* solver = nullptr;  // cusolverDnHandle_t
-  double *d_Jinv = nullptr, *d_newton = nullptr;
-  int* d_newton_i = nullptr;
+  double *d_Jinv = nullptr, *d_newton = nullptr, *d_lu_work = nullptr;
+  int* d_newton_i = nullptr;   // pivots + info
+  size_t newton_bytes = 0, jinv_bytes = 0, lu_work_bytes = 0;
 
   // NCCL
   void* nccl_comm = nullptr;
@@ -52,6 +53,7 @@ struct hank_ctx {
 
   // per-kernel CUDA-event timing of the sweep kernels (hank_profile / hank_kernel_times)
   bool profile = false;
+  int* d_jac_idx = nullptr; int jac_idx_cap = 0;   // lane<->column maps of hank_ks_jacobian_columns
   bool no_cluster = false;       // HANK_NO_CLUSTER=1: single-CTA primal sweeps
   bool fp_cluster = false;       // last forward primal ran on the cluster (per-column KD partials)
   double* d_xch = nullptr;       // [2][NE][lda] cluster exchange buffer

@@ -181,11 +181,11 @@ static int bt_launch(hank_ctx* c, int P, int K, const double* dr, const double* 
     if (S > 8) S = 8;
     if (S >= 2) {
       const size_t smem_t = fixed + (size_t)S * slot;
-      HANK_LAUNCH(KIND_BT, (k_backward_tangent_tma<NE, R, NT, L>), grid, NT, smem_t, M, c->tape, K, S, dr, dw, dvalT, dpol, dvf);
+      HANK_LAUNCH(KIND_BT, (k_backward_tangent_tma<NE, R, NT, L>), grid, NT, smem_t, M, c->tape, K, grid * L, S, dr, dw, dvalT, dpol, dvf);
     }
   }
   const size_t smem = (size_t)2 * L * LDA * sizeof(double);
-  HANK_LAUNCH(KIND_BT, (k_backward_tangent<NE, R, NT, L>), grid, NT, smem, M, c->tape, K, dr, dw, dvalT, dpol, dvf);
+  HANK_LAUNCH(KIND_BT, (k_backward_tangent<NE, R, NT, L>), grid, NT, smem, M, c->tape, K, grid * L, dr, dw, dvalT, dpol, dvf);
 }
 template <int NE, int R, int NT, int L>
 static int ft_launch(hank_ctx* c, int P, int K, const double* dpol, double* dkdpart) {
@@ -199,11 +199,11 @@ static int ft_launch(hank_ctx* c, int P, int K, const double* dpol, double* dkdp
     if (S > 8) S = 8;
     if (S >= 2) {
       const size_t smem_t = fixed + (size_t)S * slot;
-      HANK_LAUNCH(KIND_FT, (k_forward_tangent_tma<NE, R, NT, L>), grid, NT, smem_t, M, c->tape, K, S, dpol, nullptr, dkdpart, nullptr);
+      HANK_LAUNCH(KIND_FT, (k_forward_tangent_tma<NE, R, NT, L>), grid, NT, smem_t, M, c->tape, K, grid * L, S, dpol, nullptr, dkdpart, nullptr);
     }
   }
   const size_t smem = (size_t)4 * L * LDA * sizeof(double);
-  HANK_LAUNCH(KIND_FT, (k_forward_tangent<NE, R, NT, L>), grid, NT, smem, M, c->tape, K, dpol, nullptr, dkdpart, nullptr);
+  HANK_LAUNCH(KIND_FT, (k_forward_tangent<NE, R, NT, L>), grid, NT, smem, M, c->tape, K, grid * L, dpol, nullptr, dkdpart, nullptr);
 }
 
 #define TANGENT_DISPATCH(FN, ...)                                                         \

@@ -303,10 +303,22 @@ extern "C" int hank_newton_solve(hank_ctx* c, const double* Jbar, const double* 
   // workspace
   const size_t nvec = 7, extra = (size_t)kSplit * n + 16 + (size_t)(kRestartMax + 1) * n +
                                  (size_t)(kRestartMax + 1) * kRestartMax + 8 + (kRestartMax + 1);
-  if (c->d_newton) { cudaFree(c->d_newton); c->d_newton = nullptr; }
-  if (c->d_Jinv) { cudaFree(c->d_Jinv); c->d_Jinv = nullptr; }
-  CK(cudaMalloc((void**)&c->d_newton, (nvec * n + extra) * sizeof(double)));
-  CK(cudaMalloc((void**)&c->d_Jinv, nn * sizeof(double) * (solver == 1 ? 2 : 1)));
+  // workspaces persist across solves (cudaMalloc / cudaFree next to multi-GB lane buffers cost milliseconds)
+  const size_t need_vec = (nvec * n + extra) * sizeof(double), need_j = nn * sizeof(double) * 2;
+  if (c->newton_bytes < need_vec) {
+    if (c->d_newton) cudaFree(c->d_newton);
+    c->d_newton = nullptr; c->newton_bytes = 0;
+    CK(cudaMalloc((void**)&c->d_newton, need_vec));
+    c->newton_bytes = need_vec;
+  }
+  if (c->jinv_bytes < need_j) {
+    if (c->d_Jinv) cudaFree(c->d_Jinv);
+    if (c->d_newton_i) cudaFree(c->d_newton_i);
+    c->d_Jinv = nullptr; c->d_newton_i = nullptr; c->jinv_bytes = 0;
+    CK(cudaMalloc((void**)&c->d_Jinv, need_j));
+    CK(cudaMalloc((void**)&c->d_newton_i, sizeof(int) * (n + 1)));
+    c->jinv_bytes = need_j;
+  }
   double* Jx = nullptr;  // J(x), column-major, for the batched mode (reuses the LU scratch half)
   if (batched) Jx = c->d_Jinv + nn;
   NewtonBufs B;
@@ -334,9 +346,14 @@ extern "C" int hank_newton_solve(hank_ctx* c, const double* Jbar, const double* 
     int lwork = 0;
     if (cusolverDnDgetrf_bufferSize(h, n, n, LU, n, &lwork) != CUSOLVER_STATUS_SUCCESS)
       return set_error(c, HANK_ERR_CUDA, "cusolverDnDgetrf_bufferSize failed");
-    double* work = nullptr; int* ipiv = nullptr;
-    CK(cudaMalloc((void**)&work, sizeof(double) * std::max(lwork, 1)));
-    CK(cudaMalloc((void**)&ipiv, sizeof(int) * (n + 1)));
+    const size_t need_w = sizeof(double) * std::max(lwork, 1);
+    if (c->lu_work_bytes < need_w) {
+      if (c->d_lu_work) cudaFree(c->d_lu_work);
+      c->d_lu_work = nullptr; c->lu_work_bytes = 0;
+      CK(cudaMalloc((void**)&c->d_lu_work, need_w));
+      c->lu_work_bytes = need_w;
+    }
+    double* work = c->d_lu_work; int* ipiv = c->d_newton_i;
     int* info = ipiv + n;
     cusolverStatus_t s1 = cusolverDnDgetrf(h, n, n, LU, n, work, ipiv, info);
     k_identity<<<(unsigned)((nn + 255) / 256), 256, 0, c->stream>>>(B.J, n);
@@ -345,7 +362,6 @@ extern "C" int hank_newton_solve(hank_ctx* c, const double* Jbar, const double* 
     int h_info = 0;
     CK(cudaMemcpyAsync(&h_info, info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    cudaFree(work); cudaFree(ipiv);
     if (s1 != CUSOLVER_STATUS_SUCCESS || s2 != CUSOLVER_STATUS_SUCCESS || h_info != 0)
       return set_error(c, HANK_ERR_CUDA, "LU factorisation of Jbar failed (singular or cuSOLVER error)");
   }

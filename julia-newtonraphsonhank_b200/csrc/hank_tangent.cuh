@@ -17,11 +17,11 @@ namespace hank {
 // Backward tangent sweep: per period t = P..1 and lane l
 //   ĖV = V̇⁺ Πᵀ;  k̇ = a1·ĖV + kr·ṙ − ρ z ẇ;  ṗ = cA·k̇[i] + cB·k̇[i+1];  V̇ = E1·ṙ + vf·(z ẇ − ṗ)
 // CTA b carries lanes [b*L, b*L+L). smem: kb[2][L][LDA].
-// dr/dw: [K][P]; dvalT: [K][NE][LDA] or null; dpol: [P][NE][K][LDA].
+// dr/dw: [K][P]; dvalT: [K][NE][LDA] or null; dpol: [P][NE][Kp][LDA].
 // ======================================================================================
 template <int NE, int R, int NT, int L>
 __global__ void __launch_bounds__(NT, 1)
-k_backward_tangent(const Consts<NE> M, const Tape tp, int K, const double* __restrict__ dr,
+k_backward_tangent(const Consts<NE> M, const Tape tp, int K, int Kp, const double* __restrict__ dr,
                    const double* __restrict__ dw, const double* __restrict__ dvalT,
                    double* __restrict__ dpol, double* __restrict__ dvalue_first) {
   constexpr int LDA = NT * R;
@@ -100,7 +100,7 @@ k_backward_tangent(const Consts<NE> M, const Tape tp, int K, const double* __res
         }
       __syncthreads();
       const double ze = M.z[e];
-      double* dpc = dpol + (((size_t)t * NE + e) * K + lane0) * LDA + tid;
+      double* dpc = dpol + (((size_t)t * NE + e) * Kp + lane0) * LDA + tid;
 #pragma unroll
       for (int j = 0; j < R; ++j)
         if (rowok[j]) {
@@ -187,11 +187,11 @@ __device__ __forceinline__ void gather_row(const double* __restrict__ xb, const 
 // Forward tangent sweep: per period t = 1..P and lane l
 //   ẋ = ω Ḋ + (D/Δg) ṗ, ẏ = Ḋ − ẋ;  ṫmp[row] = Σ_{m=row} ẋ + Σ_{m=row+1} ẏ;  Ḋ⁺ = ṫmp Π
 //   K̇D_t = <ṗ_t, D_t> + <p_t, Ḋ_t>
-// smem: Xb[2][L][LDA] | Yb[2][L][LDA].  dpol: [P][NE][K][LDA].  dkdpart: [K][P][NT/32]
+// smem: Xb[2][L][LDA] | Yb[2][L][LDA].  dpol: [P][NE][Kp][LDA].  dkdpart: [K][P][NT/32]
 // ======================================================================================
 template <int NE, int R, int NT, int L>
 __global__ void __launch_bounds__(NT, 1)
-k_forward_tangent(const Consts<NE> M, const Tape tp, int K, const double* __restrict__ dpol,
+k_forward_tangent(const Consts<NE> M, const Tape tp, int K, int Kp, const double* __restrict__ dpol,
                   const double* __restrict__ dD0, double* __restrict__ dkdpart, double* __restrict__ dD_last) {
   constexpr int LDA = NT * R, U = 2;
   constexpr size_t GP = (size_t)NE * LDA;
@@ -223,7 +223,7 @@ k_forward_tangent(const Consts<NE> M, const Tape tp, int K, const double* __rest
   auto load_col = [&](int t, int e, double (&c)[R][FW_NF], double (&pd)[L][R], int (&s)[R][3]) {
     const double* fwt = fw_fields<LDA>(tp, NE, t, e) + tid;
     const int* st = fw_start<LDA>(tp, NE, t, e) + tid + 1;
-    const double* dpc = dpol + (((size_t)t * NE + e) * K + lane0) * LDA + tid;
+    const double* dpc = dpol + (((size_t)t * NE + e) * Kp + lane0) * LDA + tid;
 #pragma unroll
     for (int j = 0; j < R; ++j) {
 #pragma unroll

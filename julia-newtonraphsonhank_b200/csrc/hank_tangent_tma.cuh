@@ -11,6 +11,10 @@
 // algorithm needs anyway doubles as the "slot is free" signal, so no second barrier set and no
 // extra producer warp (which would cost 24 registers per thread at 512+32 threads) is needed.
 // Compute threads never issue a global load inside the period loop.
+//
+// Bookkeeping is kept off the per-point path: policy tangents use a lane stride Kp padded to a
+// multiple of L (no per-lane store predicates), rows beyond n_a run on the zero padding of the
+// tape (no per-row branches), and all chunk / slot addresses advance incrementally.
 #pragma once
 #include "hank_tangent.cuh"
 
@@ -52,10 +56,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // smem: ring[S][bw chunk] | kb[2][L][LDA] | drs[L][P] | dws[L][P] | rhos[P] | full[S]
 // Slot c%S is read in both phases of column c, so it is free after the barrier of column c+1:
 // chunk c+S-1 is issued there (prefetch distance S-1 columns).
+// dpol: [P][NE][Kp][LDA], Kp a multiple of L (lanes >= K carry zero seeds).
 // ======================================================================================
 template <int NE, int R, int NT, int L>
 __global__ void __launch_bounds__(NT, 1)
-k_backward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int S, const double* __restrict__ dr,
+k_backward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int Kp, int S, const double* __restrict__ dr,
                        const double* __restrict__ dw, const double* __restrict__ dvalT,
                        double* __restrict__ dpol, double* __restrict__ dvalue_first) {
   constexpr int LDA = NT * R, NW = NT / 32;
@@ -93,12 +98,10 @@ k_backward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int S, const do
       mbar_expect_tx(&full[c], CH);
       bulk_g2s(ring + (size_t)c * SLOT_D, tp.bw + ((size_t)(P - 1 - c / NE) * NE + c % NE) * CH, CH, &full[c]);
     }
-  // issue cursor (used by whichever thread issues): chunk ci -> (ti, ei), slot si
-  int ci = S - 1, ti = P - 1 - (S - 1) / NE, ei = (S - 1) % NE, si = S - 1;
+  // issue cursor: next chunk to request, its source and its slot
+  int ci = S - 1, ei = (S - 1) % NE, si = S - 1;
+  const unsigned char* isrc = tp.bw + ((size_t)(P - 1 - (S - 1) / NE) * NE + ei) * CH;
 
-  bool rowok[R];
-#pragma unroll
-  for (int j = 0; j < R; ++j) rowok[j] = tid + j * NT < n_a;
   double Vd[L][R][NE];
 #pragma unroll
   for (int l = 0; l < L; ++l)
@@ -106,9 +109,12 @@ k_backward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int S, const do
     for (int j = 0; j < R; ++j)
 #pragma unroll
       for (int e = 0; e < NE; ++e)
-        Vd[l][j][e] = (dvalT && rowok[j] && lane0 + l < K)
+        Vd[l][j][e] = (dvalT && tid + j * NT < n_a && lane0 + l < K)
             ? dvalT[(size_t)(lane0 + l) * GP + e * LDA + j * NT + tid] : 0.0;
 
+  const size_t strideKL = (size_t)Kp * LDA;                        // doubles between columns of dpol
+  double* dp_t = dpol + ((size_t)(P - 1) * NE * Kp + lane0) * LDA + tid;
+  const double* sl = ring + tid;                                   // current slot, this thread's row
   int slot = 0, par = 0, pb = 0, iw = 0;
   for (int t = P - 1; t >= 0; --t) {
     const double rho = rhos[t];
@@ -133,49 +139,48 @@ k_backward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int S, const do
       }
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
-      const double* sl = ring + (size_t)slot * SLOT_D + tid;
-      const int* sli = reinterpret_cast<const int*>(ring + (size_t)slot * SLOT_D + BW_NF * LDA) + tid;
+      const int* sli = reinterpret_cast<const int*>(sl - tid + BW_NF * LDA) + tid;
       double* kb = kbuf + (size_t)pb * L * LDA;
       mbar_wait(&full[slot], par);
       const double cw = -(rho * M.z[e]);
 #pragma unroll
-      for (int j = 0; j < R; ++j)
-        if (rowok[j]) {
-          const double a1 = sl[BW_A1 * LDA + j * NT], kr = sl[BW_KR * LDA + j * NT];
+      for (int j = 0; j < R; ++j) {
+        const double a1 = sl[BW_A1 * LDA + j * NT], kr = sl[BW_KR * LDA + j * NT];
 #pragma unroll
-          for (int l = 0; l < L; ++l)
-            kb[l * LDA + j * NT + tid] = fma(a1, Vd[l][j][e], fma(kr, drl[l], cw * dwl[l]));
-        }
+        for (int l = 0; l < L; ++l)
+          kb[l * LDA + j * NT + tid] = fma(a1, Vd[l][j][e], fma(kr, drl[l], cw * dwl[l]));
+      }
       __syncthreads();
       // every thread has finished reading the previous column's slot: refill it S-1 columns ahead
       if (ci < nchunks) {
         if (warp == iw && lane == 0) {
           mbar_expect_tx(&full[si], CH);
-          bulk_g2s(ring + (size_t)si * SLOT_D, tp.bw + ((size_t)ti * NE + ei) * CH, CH, &full[si]);
+          bulk_g2s(ring + (size_t)si * SLOT_D, isrc, CH, &full[si]);
         }
         ++ci;
-        if (++ei == NE) { ei = 0; --ti; }
+        if (++ei == NE) { ei = 0; isrc -= (size_t)(2 * NE - 1) * CH; } else isrc += CH;
         if (++si == S) si = 0;
         if (++iw == NW) iw = 0;
       }
       const double ze = M.z[e];
-      double* dpc = dpol + (((size_t)t * NE + e) * K + lane0) * LDA + tid;
+      double* dpc = dp_t + (size_t)e * strideKL;
 #pragma unroll
-      for (int j = 0; j < R; ++j)
-        if (rowok[j]) {
-          const double cA = sl[BW_CA * LDA + j * NT], cB = sl[BW_CB * LDA + j * NT];
-          const double E1 = sl[BW_E1 * LDA + j * NT], vf = sl[BW_VF * LDA + j * NT];
-          const double* kk = kb + sli[j * NT];
+      for (int j = 0; j < R; ++j) {
+        const double cA = sl[BW_CA * LDA + j * NT], cB = sl[BW_CB * LDA + j * NT];
+        const double E1 = sl[BW_E1 * LDA + j * NT], vf = sl[BW_VF * LDA + j * NT];
+        const double* kk = kb + sli[j * NT];
 #pragma unroll
-          for (int l = 0; l < L; ++l) {
-            const double pd = fma(cA, kk[l * LDA], cB * kk[l * LDA + 1]);
-            if (lane0 + l < K) __stcs(dpc + (size_t)l * LDA + j * NT, pd);
-            Vd[l][j][e] = fma(vf, fma(ze, dwl[l], -pd), E1 * drl[l]);
-          }
+        for (int l = 0; l < L; ++l) {
+          const double pd = fma(cA, kk[l * LDA], cB * kk[l * LDA + 1]);
+          __stcs(dpc + (size_t)l * LDA + j * NT, pd);
+          Vd[l][j][e] = fma(vf, fma(ze, dwl[l], -pd), E1 * drl[l]);
         }
+      }
       pb ^= 1;
-      if (++slot == S) { slot = 0; par ^= 1; }
+      sl += SLOT_D;
+      if (++slot == S) { slot = 0; par ^= 1; sl -= (size_t)S * SLOT_D; }
     }
+    dp_t -= (size_t)NE * strideKL;
   }
   if (dvalue_first) {
 #pragma unroll
@@ -183,7 +188,7 @@ k_backward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int S, const do
       if (lane0 + l < K)
 #pragma unroll
         for (int j = 0; j < R; ++j)
-          if (rowok[j])
+          if (tid + j * NT < n_a)
 #pragma unroll
             for (int e = 0; e < NE; ++e)
               dvalue_first[(size_t)(lane0 + l) * GP + e * LDA + j * NT + tid] = Vd[l][j][e];
@@ -198,7 +203,7 @@ k_backward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int S, const do
 // ======================================================================================
 template <int NE, int R, int NT, int L>
 __global__ void __launch_bounds__(NT, 1)
-k_forward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int S, const double* __restrict__ dpol,
+k_forward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int Kp, int S, const double* __restrict__ dpol,
                       const double* __restrict__ dD0, double* __restrict__ dkdpart,
                       double* __restrict__ dD_last) {
   constexpr int LDA = NT * R, U = 2, NW = NT / 32;
@@ -206,6 +211,7 @@ k_forward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int S, const dou
   constexpr int CH = (int)fw_chunk_bytes<LDA>();
   constexpr int PD_OFF = CH / 8;                 // ṗ lanes follow the chunk (CH is a multiple of 16)
   constexpr int SLOT_D = PD_OFF + L * LDA;
+  constexpr uint32_t PDB = (uint32_t)L * LDA * 8;
   extern __shared__ __align__(128) unsigned char smem_tma[];
   const int n_a = M.n_a, P = M.P;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -215,31 +221,26 @@ k_forward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int S, const dou
   double* Yb = Xb + 2 * L * LDA;
   uint64_t* full = reinterpret_cast<uint64_t*>(Yb + 2 * L * LDA);
   const int nchunks = P * NE;
-  int nl = K - lane0;  // live lanes of this CTA
-  if (nl > L) nl = L;
-  const uint32_t pd_bytes = (uint32_t)(nl * LDA * 8);
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  // lanes beyond K read zeros from their (never filled) ṗ slots
-  for (int i = tid; i < S * SLOT_D; i += NT) ring[i] = 0.0;
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
-  auto issue = [&](int t, int e, int s) {
+  // chunk c = t*NE + e: the tape chunk at tp.fw + c*CH and ṗ at dpol + (c*Kp + lane0)*LDA
+  const size_t strideKL = (size_t)Kp * LDA;
+  const double* psrc0 = dpol + (size_t)lane0 * LDA;
+  auto issue = [&](int c, int s) {
     double* dst = ring + (size_t)s * SLOT_D;
-    mbar_expect_tx(&full[s], (uint32_t)CH + pd_bytes);
-    bulk_g2s(dst, tp.fw + ((size_t)t * NE + e) * CH, CH, &full[s]);
-    bulk_g2s(dst + PD_OFF, dpol + (((size_t)t * NE + e) * K + lane0) * LDA, pd_bytes, &full[s]);
+    mbar_expect_tx(&full[s], (uint32_t)CH + PDB);
+    bulk_g2s(dst, tp.fw + (size_t)c * CH, CH, &full[s]);
+    bulk_g2s(dst + PD_OFF, psrc0 + (size_t)c * strideKL, PDB, &full[s]);
   };
   if (tid == 0)
-    for (int c = 0; c < S && c < nchunks; ++c) issue(c / NE, c % NE, c);
-  int ci = S, ti = S / NE, ei = S % NE, si = 0;
+    for (int c = 0; c < S && c < nchunks; ++c) issue(c, c);
+  int ci = S, si = 0;
 
-  bool rowok[R];
-#pragma unroll
-  for (int j = 0; j < R; ++j) rowok[j] = tid + j * NT < n_a;
   double Dd[L][R][NE];
 #pragma unroll
   for (int l = 0; l < L; ++l)
@@ -247,8 +248,9 @@ k_forward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int S, const dou
     for (int j = 0; j < R; ++j)
 #pragma unroll
       for (int e = 0; e < NE; ++e)
-        Dd[l][j][e] = (dD0 && rowok[j] && lane0 + l < K) ? dD0[(size_t)(lane0 + l) * GP + e * LDA + j * NT + tid] : 0.0;
+        Dd[l][j][e] = (dD0 && tid + j * NT < n_a && lane0 + l < K) ? dD0[(size_t)(lane0 + l) * GP + e * LDA + j * NT + tid] : 0.0;
 
+  const double* sl = ring + tid;
   int slot = 0, par = 0, pb = 0, iw = 0;
   for (int t = 0; t < P; ++t) {
     double kacc[L];
@@ -257,35 +259,29 @@ k_forward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int S, const dou
     double pv[R][NE];  // p_t of the row, picked up column by column for <p_t, Ḋ_t>
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
-      const double* sl = ring + (size_t)slot * SLOT_D + tid;
-      const int* sst = reinterpret_cast<const int*>(ring + (size_t)slot * SLOT_D + FW_NF * LDA) + tid + 1;
+      const int* sst = reinterpret_cast<const int*>(sl - tid + FW_NF * LDA) + tid + 1;
       double* xb = Xb + (size_t)pb * L * LDA;
       double* yb = Yb + (size_t)pb * L * LDA;
       mbar_wait(&full[slot], par);
       int s0[R], s1[R], s2[R];
 #pragma unroll
       for (int j = 0; j < R; ++j) {
-        s0[j] = s1[j] = s2[j] = 0;
-        pv[j][e] = 0.0;
-        if (rowok[j]) {
-          const double om = sl[FW_OM * LDA + j * NT], dco = sl[FW_DCO * LDA + j * NT], Dn = sl[FW_D * LDA + j * NT];
-          pv[j][e] = sl[FW_P * LDA + j * NT];
-          s0[j] = sst[j * NT]; s1[j] = sst[j * NT + 1]; s2[j] = sst[j * NT + 2];
+        const double om = sl[FW_OM * LDA + j * NT], dco = sl[FW_DCO * LDA + j * NT], Dn = sl[FW_D * LDA + j * NT];
+        pv[j][e] = sl[FW_P * LDA + j * NT];
+        s0[j] = sst[j * NT]; s1[j] = sst[j * NT + 1]; s2[j] = sst[j * NT + 2];
 #pragma unroll
-          for (int l = 0; l < L; ++l) {
-            const double pd = sl[PD_OFF + l * LDA + j * NT];
-            const double xd = fma(om, Dd[l][j][e], dco * pd);
-            xb[l * LDA + j * NT + tid] = xd;
-            yb[l * LDA + j * NT + tid] = Dd[l][j][e] - xd;
-            kacc[l] = fma(pd, Dn, kacc[l]);
-          }
+        for (int l = 0; l < L; ++l) {
+          const double pd = sl[PD_OFF + l * LDA + j * NT];
+          const double xd = fma(om, Dd[l][j][e], dco * pd);
+          xb[l * LDA + j * NT + tid] = xd;
+          yb[l * LDA + j * NT + tid] = Dd[l][j][e] - xd;
+          kacc[l] = fma(pd, Dn, kacc[l]);
         }
       }
       __syncthreads();
       if (ci < nchunks) {   // this column's slot is free again: refill it S columns ahead
-        if (warp == iw && lane == 0) issue(ti, ei, si);
+        if (warp == iw && lane == 0) issue(ci, si);
         ++ci;
-        if (++ei == NE) { ei = 0; ++ti; }
         if (++si == S) si = 0;
         if (++iw == NW) iw = 0;
       }
@@ -297,26 +293,26 @@ k_forward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int S, const dou
         for (int l = 0; l < L; ++l) Dd[l][j][e] = acc[l];
       }
       pb ^= 1;
-      if (++slot == S) { slot = 0; par ^= 1; }
+      sl += SLOT_D;
+      if (++slot == S) { slot = 0; par ^= 1; sl -= (size_t)S * SLOT_D; }
     }
     // ---- Markov mix (in place) and second aggregation term <p_t, Ḋ_t>
 #pragma unroll
-    for (int j = 0; j < R; ++j)
-      if (rowok[j]) {
+    for (int j = 0; j < R; ++j) {
 #pragma unroll
-        for (int l = 0; l < L; ++l) {
-          double d[NE];
+      for (int l = 0; l < L; ++l) {
+        double d[NE];
 #pragma unroll
-          for (int e2 = 0; e2 < NE; ++e2) {
-            double s = 0.0;
+        for (int e2 = 0; e2 < NE; ++e2) {
+          double s = 0.0;
 #pragma unroll
-            for (int e = 0; e < NE; ++e) s = fma(M.Pi[e][e2], Dd[l][j][e], s);
-            d[e2] = s;
-          }
-#pragma unroll
-          for (int e2 = 0; e2 < NE; ++e2) { Dd[l][j][e2] = d[e2]; kacc[l] = fma(pv[j][e2], d[e2], kacc[l]); }
+          for (int e = 0; e < NE; ++e) s = fma(M.Pi[e][e2], Dd[l][j][e], s);
+          d[e2] = s;
         }
+#pragma unroll
+        for (int e2 = 0; e2 < NE; ++e2) { Dd[l][j][e2] = d[e2]; kacc[l] = fma(pv[j][e2], d[e2], kacc[l]); }
       }
+    }
 #pragma unroll
     for (int l = 0; l < L; ++l) {
       const double s = warp_sum(kacc[l]);
@@ -329,7 +325,7 @@ k_forward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int S, const dou
       if (lane0 + l < K)
 #pragma unroll
         for (int j = 0; j < R; ++j)
-          if (rowok[j])
+          if (tid + j * NT < n_a)
 #pragma unroll
             for (int e = 0; e < NE; ++e)
               dD_last[(size_t)(lane0 + l) * GP + e * LDA + j * NT + tid] = Dd[l][j][e];
