@@ -138,7 +138,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="hankb200", choices=["hankb200", "reference"])
     ap.add_argument("--workload", default="ks_500x7_T300", choices=sorted(WORKLOADS))
-    ap.add_argument("--lanes", type=int, default=592, help="tangent lanes per GPU per step (4 per SM x 148 SMs)")
+    ap.add_argument("--lanes", type=int, default=1184, help="tangent lanes per GPU per step (2 waves of 4 lanes x 148 SMs; the full T=300 Jacobian has 1196 columns)")
     ap.add_argument("--cpu-lanes", type=int, default=32, help="lanes per step of the CPU sample")
     ap.add_argument("--no-newton", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -17,6 +17,9 @@
 // tape (no per-row branches), and all chunk / slot addresses advance incrementally.
 #pragma once
 #include "hank_tangent.cuh"
+#ifndef HANK_GATHER_U
+#define HANK_GATHER_U 2
+#endif
 
 namespace hank {
 
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(NT, 1)
 k_forward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int Kp, int S, const double* __restrict__ dpol,
                       const double* __restrict__ dD0, double* __restrict__ dkdpart,
                       double* __restrict__ dD_last) {
-  constexpr int LDA = NT * R, U = 2, NW = NT / 32;
+  constexpr int LDA = NT * R, U = HANK_GATHER_U, NW = NT / 32;
   constexpr size_t GP = (size_t)NE * LDA;
   constexpr int CH = (int)fw_chunk_bytes<LDA>();
   constexpr int PD_OFF = CH / 8;                 // ṗ lanes follow the chunk (CH is a multiple of 16)
