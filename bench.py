@@ -138,7 +138,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="hankb200", choices=["hankb200", "reference"])
     ap.add_argument("--workload", default="ks_500x7_T300", choices=sorted(WORKLOADS))
-    ap.add_argument("--lanes", type=int, default=1184, help="tangent lanes per GPU per step (2 waves of 4 lanes x 148 SMs; the full T=300 Jacobian has 1196 columns)")
+    ap.add_argument("--lanes", type=int, default=1156, help="tangent lanes per GPU per step: 4 lanes x (2 x 148 - 7) CTAs = two waves with the 7-CTA forward-primal cluster overlapped in the first; the full T=300 Jacobian has 1196 columns")
     ap.add_argument("--cpu-lanes", type=int, default=32, help="lanes per step of the CPU sample")
     ap.add_argument("--no-newton", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -253,7 +253,8 @@ def main():
     prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get(args.workload, {}).get(dom)
+            per_lane = json.load(open(prof)).get(args.workload, {}).get(dom + "_bytes_per_lane")
+            traffic = per_lane * K if per_lane else None
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,

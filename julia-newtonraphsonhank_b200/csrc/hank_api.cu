@@ -180,7 +180,18 @@ static int dalloc(hank_ctx* c, T** p, size_t count) {
 template <typename T>
 static void dfree(T*& p) { if (p) cudaFree(p); p = nullptr; }
 
+// Work queued on the side stream (forward primal sweep + residuals of the last linearisation) must be
+// complete before anything on the main stream reads its results or overwrites its inputs.
+static int join_side(hank_ctx* c) {
+  if (c->fp_pending) {
+    CK(cudaStreamWaitEvent(c->stream, c->ev_fp, 0));
+    c->fp_pending = false;
+  }
+  return HANK_OK;
+}
+
 static int check_status(hank_ctx* c) {
+  RC(join_side(c));
   CK(cudaMemcpyAsync(c->h_status, c->d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   const int code = c->h_status[0];
@@ -257,6 +268,7 @@ static int copy_out(hank_ctx* c, T* dst_dense, const T* src_padded, size_t rows)
 // Tangent pass over the current tape for lanes given by dr/dw (already on device, [K][P]).
 static int tangent_pass(hank_ctx* c, int P, int K) {
   RC(sw_backward_tangent(c, P, K, c->d_dr, c->d_dw, nullptr, c->d_dpol, nullptr));
+  RC(join_side(c));  // the forward tangent needs the forward tape of the linearisation
   int nw = 16;
   RC(sw_forward_tangent(c, P, K, c->d_dpol, c->d_dkdpart, &nw));
   k_reduce_partials<<<nblk((size_t)K * P), 256, 0, c->stream>>>(c->d_dkdpart, nw, K * P, c->d_dKD);
@@ -306,6 +318,14 @@ int hank_ctx_create(hank_ctx** out, int device, int n_a, int n_e, int T, const d
   { const char* nt = getenv("HANK_NO_WIDE"); c->no_wide = nt && nt[0] == '1'; }
   { const char* nt = getenv("HANK_NO_CLUSTER"); c->no_cluster = nt && nt[0] == '1'; }
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, hi));
+    CK(cudaEventCreateWithFlags(&c->ev_bp, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_fp, cudaEventDisableTiming));
+    const char* nv = getenv("HANK_NO_OVERLAP"); c->no_overlap = nv && nv[0] == '1';
+  }
   CK(cudaEventCreate(&c->ev0));
   CK(cudaEventCreate(&c->ev1));
   const size_t PG = (size_t)c->P * c->Gp;
@@ -333,6 +353,9 @@ int hank_ctx_create(hank_ctx** out, int device, int n_a, int n_e, int T, const d
 void hank_ctx_destroy(hank_ctx* c) {
   if (!c) return;
   if (c->stream) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
+  if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
+  if (c->ev_bp) cudaEventDestroy(c->ev_bp);
+  if (c->ev_fp) cudaEventDestroy(c->ev_fp);
   hank_comm_destroy(c);
   Tape& tp = c->tape;
   dfree(c->d_grid); dfree(c->d_valueT); dfree(c->d_D0); dfree(c->d_r); dfree(c->d_w);
@@ -361,6 +384,7 @@ int hank_sync(hank_ctx* c) {
 }
 int hank_timer_start(hank_ctx* c) { CK(cudaEventRecord(c->ev0, c->stream)); return HANK_OK; }
 int hank_timer_stop(hank_ctx* c, float* ms) {
+  RC(join_side(c));
   CK(cudaEventRecord(c->ev1, c->stream));
   CK(cudaEventSynchronize(c->ev1));
   CK(cudaEventElapsedTime(ms, c->ev0, c->ev1));
@@ -375,6 +399,7 @@ int hank_profile(hank_ctx* c, int enable) {
 int hank_kernel_times(hank_ctx* c, double* ms4, int64_t* count4, int reset) {
   if (!c) return HANK_ERR_ARG;
   CK(cudaSetDevice(c->device));
+  RC(join_side(c));
   CK(cudaStreamSynchronize(c->stream));
   for (auto& r : c->recs) {
     float ms = 0.f;
@@ -412,6 +437,7 @@ int hank_set_initial_dist(hank_ctx* c, const double* D0) {
 
 // ---- sweeps ------------------------------------------------------------------------------
 static int backward_dev(hank_ctx* c, const double* r, const double* w, int K, const double* dr, const double* dw) {
+  RC(join_side(c));
   if (!c->have_terminal) return set_error(c, HANK_ERR_STATE, "hank_set_terminal has not been called");
   if (K < 0 || (K > 0 && (!dr || !dw))) return set_error(c, HANK_ERR_ARG, "K > 0 needs dr and dw");
   RC(sw_backward_primal(c, c->P, c->d_valueT, r, w));
@@ -479,6 +505,7 @@ int hank_forward(hank_ctx* c, double* KD, double* dKD) {
 
 int hank_forward_policies(hank_ctx* c, const double* policy, int K, const double* dpolicy, double* KD, double* dKD) {
   CK(cudaSetDevice(c->device));
+  RC(join_side(c));
   const int P = c->P;
   if (K > 0) { RC(ensure_lanes(c, K)); if (K > c->Kcap) return set_error(c, HANK_ERR_ARG, "K exceeds device memory"); }
   RC(copy_in(c, c->tape.pol, policy, (size_t)P * c->n_e));
@@ -502,6 +529,7 @@ int hank_block(hank_ctx* c, const double* r, const double* w, int K, const doubl
 int hank_egm_step(hank_ctx* c, const double* value_next, const double* dvalue_next, double r, double w, int K,
                   const double* dr, const double* dw, double* value, double* policy, double* dvalue, double* dpolicy) {
   CK(cudaSetDevice(c->device));
+  RC(join_side(c));
   if (K < 0 || (K > 0 && (!dr || !dw))) return set_error(c, HANK_ERR_ARG, "K > 0 needs dr and dw");
   if (K > 0) RC(ensure_lanes(c, K));
   if (K > c->Kcap && K > 0) return set_error(c, HANK_ERR_ARG, "K exceeds device memory");
@@ -557,6 +585,7 @@ __global__ void k_max_abs_diff(const double* __restrict__ a, const double* __res
 int hank_vfi(hank_ctx* c, double r, double w, int K, const double* dr, const double* dw, double eps, int max_iter,
              double* value, double* policy, double* dvalue, double* dpolicy, int* iters) {
   CK(cudaSetDevice(c->device));
+  RC(join_side(c));
   if (K < 0 || (K > 0 && (!dr || !dw))) return set_error(c, HANK_ERR_ARG, "K > 0 needs dr and dw");
   if (K > 0) RC(ensure_lanes(c, K));
   if (K > c->Kcap && K > 0) return set_error(c, HANK_ERR_ARG, "K exceeds device memory");
@@ -621,6 +650,7 @@ int hank_get_policy(hank_ctx* c, int t, int lane, double* out) {
 }
 int hank_get_dist(hank_ctx* c, int t, double* out) {
   CK(cudaSetDevice(c->device));
+  RC(join_side(c));
   if (!c->have_forward) return set_error(c, HANK_ERR_STATE, "no forward sweep has been run");
   if (t < 1 || t > c->P) return set_error(c, HANK_ERR_ARG, "t out of range");
   // D_t sits in field FW_D of each column chunk: [t][e][FW_NF][lda]
@@ -638,6 +668,7 @@ int hank_get_value_first(hank_ctx* c, int lane, double* out) {
 }
 int hank_get_brackets(hank_ctx* c, int t, int32_t* m) {
   CK(cudaSetDevice(c->device));
+  RC(join_side(c));
   if (!c->have_forward) return set_error(c, HANK_ERR_STATE, "no forward sweep has been run");
   if (t < 1 || t > c->P) return set_error(c, HANK_ERR_ARG, "t out of range");
   RC(copy_out(c, m, (const int32_t*)(c->tape.mbr + (size_t)(t - 1) * c->Gp), c->n_e));
@@ -676,10 +707,25 @@ int hank_ks_linearize_dev(hank_ctx* c, const double* x, const double* Z, double*
   k_extract_rw<<<nblk(P), 256, 0, c->stream>>>(c->d_x, P, c->d_r, c->d_w);
   c->launches++;
   RC(backward_dev(c, c->d_r, c->d_w, 0, nullptr, nullptr));
-  RC(forward_dev(c, c->tape.pol, 0, nullptr, c->d_KD, nullptr));
-  k_ks_residual<<<nblk(P), 256, 0, c->stream>>>(P, c->alpha, c->delta, c->ssKS, c->d_x, c->d_KD, c->d_Z, F);
-  c->launches++;
-  CK(cudaGetLastError());
+  // The forward primal sweep and the residuals only feed the forward tangent / F: they go to the
+  // high-priority side stream so that a following backward tangent sweep overlaps them.
+  cudaStream_t main_stream = c->stream;
+  if (!c->no_overlap) {
+    CK(cudaEventRecord(c->ev_bp, main_stream));
+    CK(cudaStreamWaitEvent(c->stream2, c->ev_bp, 0));
+    c->stream = c->stream2;
+  }
+  int rc = forward_dev(c, c->tape.pol, 0, nullptr, c->d_KD, nullptr);
+  if (rc == HANK_OK) {
+    k_ks_residual<<<nblk(P), 256, 0, c->stream>>>(P, c->alpha, c->delta, c->ssKS, c->d_x, c->d_KD, c->d_Z, F);
+    c->launches++;
+    rc = cuda_check(c, cudaGetLastError(), "k_ks_residual");
+  }
+  if (!c->no_overlap) {
+    c->stream = main_stream;
+    if (rc == HANK_OK) { CK(cudaEventRecord(c->ev_fp, c->stream2)); c->fp_pending = true; }
+  }
+  RC(rc);
   c->linearized = true;
   return HANK_OK;
 }
@@ -711,6 +757,7 @@ int hank_ks_linearize(hank_ctx* c, const double* x, const double* Z, double* F) 
   CK(cudaMemcpyAsync(c->d_x, x, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_Z, Z, P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   RC(hank_ks_linearize_dev(c, c->d_x, c->d_Z, c->d_F));
+  RC(join_side(c));
   if (F) CK(cudaMemcpyAsync(F, c->d_F, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   int rc = check_status(c);
   if (rc) c->linearized = false;
