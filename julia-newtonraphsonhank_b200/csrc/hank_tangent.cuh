@@ -147,12 +147,13 @@ __device__ __forceinline__ void gather_row(const double* __restrict__ xb, const 
   for (int l = 0; l < L; ++l) acc[l] = 0.0;
 #pragma unroll
   for (int d = 0; d < U; ++d) {
-    const bool p1 = d < n1, p2 = d < n2;
+    if (d < n1) {
 #pragma unroll
-    for (int l = 0; l < L; ++l) {
-      const double xv = p1 ? xb[l * LDA + s0 + d] : 0.0;
-      const double yv = p2 ? yb[l * LDA + s1 + d] : 0.0;
-      acc[l] += xv + yv;
+      for (int l = 0; l < L; ++l) acc[l] += xb[l * LDA + s0 + d];
+    }
+    if (d < n2) {
+#pragma unroll
+      for (int l = 0; l < L; ++l) acc[l] += yb[l * LDA + s1 + d];
     }
   }
   // a few more sources: finish in this thread; long ranges: the whole warp, one row at a time
