@@ -11,7 +11,7 @@ With --gpus N (one process per GPU, torchrun) every rank carries K lanes (weak s
 n x K column blocks are all-gathered with NCCL (hank_allgather_columns_dev).
 
 Prints ONE JSON line (rank 0).  `value` has inputs resident in HBM; `e2e` goes through the
-host-pointer C ABI (hank_ks_linearize + hank_ks_jvp) with pinned host buffers, copies inside the
+host-pointer C ABI (hank_ks_fjvp = linearise + K-lane JVP) with pinned host buffers, copies inside the
 timed region.  `--impl reference` times the CPU oracle (single-thread C++ restatement of the
 reference's Julia path; Julia is not installed in this image) on a bounded sample.
 """
@@ -95,38 +95,57 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+_W = {}
+
+
+def _ref_worker_init(workload):
+    from oracle import oracle as O
+    fx = load_fixture(workload); g = fx["g"]
+    _W["fx"] = fx
+    _W["orc"] = O.Oracle(g["grid"], g["z"], g["Pi"], float(g["beta"]), float(g["gamma"]), float(g["borrow_cons"]), fx["T"])
+
+
+def _ref_worker(V):
+    fx = _W["fx"]; g = fx["g"]
+    F, JV = _W["orc"].ks_fjvp(fx["ks"], g["ss_value"], g["ss_D"], fx["Z"], fx["x0"], V)
+    return float(JV.sum())
+
+
 def run_reference(args):
-    """CPU arm: the oracle (kind "port") on the same workload, bounded sample per step."""
+    """CPU arm: the oracle (kind "port") on the same workload, bounded sample per step.  The reference has no
+    threading of its own; independent JVP directions are farmed out to one process per host core (what a user
+    would do with Distributed.pmap), each process recomputing the primal like each GPU rank does."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import multiprocessing as mp
     from oracle import oracle as O
     O.build()
     fx = load_fixture(args.workload)
-    g = fx["g"]
-    orc = O.Oracle(g["grid"], g["z"], g["Pi"], float(g["beta"]), float(g["gamma"]), float(g["borrow_cons"]), fx["T"])
-    Kc = args.cpu_lanes
+    procs = max(1, args.cpu_procs or (os.cpu_count() or 1))
+    Kc = args.cpu_lanes                      # lanes per process per step
     rng = np.random.default_rng(1234)
-    V = rng.standard_normal((Kc, fx["n"]))
-    def step():
-        orc.ks_fjvp(fx["ks"], g["ss_value"], g["ss_D"], fx["Z"], fx["x0"], V)
-    for _ in range(min(args.warmup, 1)):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = time.perf_counter() - t0
-    val = Kc * args.steps / dt
-    cores = 1
-    sample = f"{Kc} of the GPU arm's {args.lanes} lanes per step (primal + {Kc} tangent lanes), {args.steps} steps"
+    Vs = [rng.standard_normal((Kc, fx["n"])) for _ in range(procs)]
+    with mp.get_context("fork").Pool(procs, initializer=_ref_worker_init, initargs=(args.workload,)) as pool:
+        def step():
+            pool.map(_ref_worker, Vs, chunksize=1)
+        for _ in range(min(args.warmup, 1)):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        dt = time.perf_counter() - t0
+    val = procs * Kc * args.steps / dt
+    sample = (f"{procs} processes x {Kc} lanes per step (each: primal + {Kc} tangent lanes) of the GPU arm's "
+              f"{args.lanes} lanes, {args.steps} steps")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "desc": WORKLOADS[args.workload]["desc"], "lanes_per_step": Kc},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                         "note": "single-thread C++ restatement of the reference CPU path; Julia is not installed "
-                                 "and the reference has no threading (host nproc=%d)" % os.cpu_count()},
+        "config": {"workload": args.workload, "desc": WORKLOADS[args.workload]["desc"], "lanes_per_step": procs * Kc},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample,
+                         "note": "C++ restatement of the reference CPU path (oracle/); Julia is not installed. The "
+                                 "reference is single-threaded: lanes are spread over one process per host core"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -139,7 +158,8 @@ def main():
     ap.add_argument("--impl", default="hankb200", choices=["hankb200", "reference"])
     ap.add_argument("--workload", default="ks_500x7_T300", choices=sorted(WORKLOADS))
     ap.add_argument("--lanes", type=int, default=1156, help="tangent lanes per GPU per step: 4 lanes x (2 x 148 - 7) CTAs = two waves with the 7-CTA forward-primal cluster overlapped in the first; the full T=300 Jacobian has 1196 columns")
-    ap.add_argument("--cpu-lanes", type=int, default=32, help="lanes per step of the CPU sample")
+    ap.add_argument("--cpu-lanes", type=int, default=32, help="lanes per step (per process in the reference arm) of the CPU sample")
+    ap.add_argument("--cpu-procs", type=int, default=0, help="processes of the reference arm (0 = one per host core)")
     ap.add_argument("--no-newton", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -193,8 +213,7 @@ def main():
             blk._ck(L.hank_allgather_columns_dev(h, vp(JVd), K * n, vp(ALLd)))
 
     def step_e2e():
-        blk._ck(L.hank_ks_linearize(h, dp(xh), dp(Zh), dp(Fh)))
-        blk._ck(L.hank_ks_jvp(h, K, dp(Vh), dp(JVh)))
+        blk._ck(L.hank_ks_fjvp(h, dp(xh), dp(Zh), K, dp(Vh), dp(Fh), dp(JVh)))
 
     def barrier():
         torch.cuda.synchronize()

@@ -131,6 +131,10 @@ int hank_ks_linearize(hank_ctx* ctx, const double* x, const double* Z, double* F
 /* JVP(fullFunction, x, V[:,k]) for K directions at the x of the last hank_ks_linearize
  * (GeneralStructures.jl:542-550).  V, JV: n x K column-major.                                */
 int hank_ks_jvp(hank_ctx* ctx, int K, const double* V, double* JV);
+/* hank_ks_linearize followed by hank_ks_jvp in one call (host buffers); the seed upload overlaps the
+ * primal backward sweep.                                                                      */
+int hank_ks_fjvp(hank_ctx* ctx, const double* x, const double* Z, int K, const double* V, double* F,
+                 double* JV);
 int hank_ks_linearize_dev(hank_ctx* ctx, const double* x, const double* Z, double* F);
 int hank_ks_jvp_dev(hank_ctx* ctx, int K, const double* V, double* JV);
 /* Columns [col_begin, col_end) (1-based, half-open on the right: col_begin..col_end-1) of the

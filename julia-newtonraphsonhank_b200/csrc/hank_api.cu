@@ -324,6 +324,8 @@ int hank_ctx_create(hank_ctx** out, int device, int n_a, int n_e, int T, const d
     CK(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, hi));
     CK(cudaEventCreateWithFlags(&c->ev_bp, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_fp, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_v, cudaEventDisableTiming));
     const char* nv = getenv("HANK_NO_OVERLAP"); c->no_overlap = nv && nv[0] == '1';
   }
   CK(cudaEventCreate(&c->ev0));
@@ -354,6 +356,8 @@ void hank_ctx_destroy(hank_ctx* c) {
   if (!c) return;
   if (c->stream) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
   if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
+  if (c->stream3) { cudaStreamSynchronize(c->stream3); cudaStreamDestroy(c->stream3); }
+  if (c->ev_v) cudaEventDestroy(c->ev_v);
   if (c->ev_bp) cudaEventDestroy(c->ev_bp);
   if (c->ev_fp) cudaEventDestroy(c->ev_fp);
   hank_comm_destroy(c);
@@ -773,6 +777,30 @@ int hank_ks_jvp(hank_ctx* c, int K, const double* V, double* JV) {
   RC(hank_ks_jvp_dev(c, K, c->d_V, c->d_JV));
   CK(cudaMemcpyAsync(JV, c->d_JV, n * K * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   return check_status(c);
+}
+
+// fullFunction(x) and JVP(fullFunction, x, V[:,k]) in one call with host buffers: the upload of the K
+// tangent seeds runs on a copy stream underneath the primal backward sweep.
+int hank_ks_fjvp(hank_ctx* c, const double* x, const double* Z, int K, const double* V, double* F, double* JV) {
+  CK(cudaSetDevice(c->device));
+  if (K < 1) return set_error(c, HANK_ERR_ARG, "K must be >= 1");
+  const int P = c->P; const size_t n = (size_t)4 * P;
+  RC(ensure_V(c, K));
+  RC(ensure_lanes(c, K));
+  RC(join_side(c));
+  CK(cudaStreamSynchronize(c->stream));   // d_V may still feed the previous call's kernels
+  CK(cudaMemcpyAsync(c->d_V, V, n * K * sizeof(double), cudaMemcpyHostToDevice, c->stream3));
+  CK(cudaEventRecord(c->ev_v, c->stream3));
+  CK(cudaMemcpyAsync(c->d_x, x, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_Z, Z, P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  RC(hank_ks_linearize_dev(c, c->d_x, c->d_Z, c->d_F));
+  CK(cudaStreamWaitEvent(c->stream, c->ev_v, 0));
+  RC(hank_ks_jvp_dev(c, K, c->d_V, c->d_JV));
+  CK(cudaMemcpyAsync(JV, c->d_JV, n * K * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (F) CK(cudaMemcpyAsync(F, c->d_F, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  int rc = check_status(c);
+  if (rc) c->linearized = false;
+  return rc;
 }
 
 int hank_ks_jacobian_columns_dev(hank_ctx* c, int col_begin, int col_end, double* J) {

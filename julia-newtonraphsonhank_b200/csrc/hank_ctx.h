@@ -15,7 +15,8 @@ struct hank_ctx {
   std::vector<double> h_grid, h_z, h_Pi;  // h_Pi row-major [e][e2]
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;   // high-priority side stream: forward primal sweep overlapping the backward tangent
-  cudaEvent_t ev_bp = nullptr, ev_fp = nullptr;
+  cudaStream_t stream3 = nullptr;   // copy stream: tangent seeds upload overlapping the primal sweep
+  cudaEvent_t ev_bp = nullptr, ev_fp = nullptr, ev_v = nullptr;
   bool fp_pending = false, no_overlap = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int smem_max = 0, sm_count = 0;

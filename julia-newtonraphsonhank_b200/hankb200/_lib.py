@@ -46,6 +46,7 @@ SIGNATURES = {
     "hank_ks_configure": (C.c_int, [ctx_p, C.c_double, C.c_double, C.c_double]),
     "hank_ks_linearize": (C.c_int, [ctx_p, c_dp, c_dp, c_dp]),
     "hank_ks_jvp": (C.c_int, [ctx_p, C.c_int, c_dp, c_dp]),
+    "hank_ks_fjvp": (C.c_int, [ctx_p, c_dp, c_dp, C.c_int, c_dp, c_dp, c_dp]),
     "hank_ks_linearize_dev": (C.c_int, [ctx_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hank_ks_jvp_dev": (C.c_int, [ctx_p, C.c_int, C.c_void_p, C.c_void_p]),
     "hank_ks_jacobian_columns": (C.c_int, [ctx_p, C.c_int, C.c_int, c_dp]),

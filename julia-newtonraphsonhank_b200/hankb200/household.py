@@ -224,6 +224,15 @@ class HouseholdBlock:
         self._ck(self._L.hank_ks_jvp(self._h, V.shape[0], _p(V), _p(JV)))
         return JV
 
+    def fjvp(self, x, Z, V):
+        """fullFunction(x) and J(x)·V in one call: returns (F, JV)."""
+        x = _f(x, (self.n,)); Z = _f(Z, (self.P,)); V = _f(V)
+        if V.ndim == 1:
+            V = V[None]
+        F = np.empty(self.n); JV = np.empty_like(V)
+        self._ck(self._L.hank_ks_fjvp(self._h, _p(x), _p(Z), V.shape[0], _p(V), _p(F), _p(JV)))
+        return F, JV
+
     def jacobian_columns(self, col_begin, col_end):
         """Columns col_begin..col_end-1 (1-based) of the Jacobian at the linearisation point,
         returned as (n, ncols) with J[:, j] the column (NumPy layout)."""

@@ -153,6 +153,14 @@ function JVP(b::HouseholdBlock, primal::Vector{Float64}, tangents::AbstractVecOr
     tangents isa AbstractVector ? sparse(vec(JV)) : JV
 end
 
+"""`(F(x), J(x)·V)` in one call (hank_ks_fjvp): the seed upload overlaps the primal backward sweep."""
+function fjvp(b::HouseholdBlock, x::Vector{Float64}, Z::Vector{Float64}, V::Matrix{Float64})
+    F = Vector{Float64}(undef, length(x)); JV = similar(V)
+    check(b, ccall((:hank_ks_fjvp, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                   b.ctx, x, Z, size(V, 2), V, F, JV))
+    (F, JV)
+end
+
 """Columns `cols` (a range) of the sequence-space Jacobian at `x`: directJVPJacobian (SteadyState.jl:296-320)
 generalised to any column range; the Y / KS columns skip the household sweeps."""
 function jacobian(b::HouseholdBlock, x::Vector{Float64}, Z::Vector{Float64}, cols::UnitRange{Int} = 1:length(x))

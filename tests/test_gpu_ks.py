@@ -54,6 +54,8 @@ def test_golden_ks_gpu(path):
     assert close(F0, g["F0"]), maxerr(F0, g["F0"])
     JV = blk.jvp(g["V"])
     assert close(JV, g["JV"]), maxerr(JV, g["JV"])
+    F2, JV2 = blk.fjvp(g["x0"], g["Z"], g["V"])           # fused host entry
+    assert np.array_equal(F2, F0) and np.array_equal(JV2, JV)
     # Jacobian columns at the steady-state path (Z = 1): unit-seed JVPs
     blk.linearize(g["x0"], np.ones(P))
     J = blk.jacobian_columns(1, n + 1)

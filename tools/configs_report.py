@@ -58,6 +58,7 @@ def model_case(fixture, label):
 
 
 ap = argparse.ArgumentParser(); ap.add_argument("--only", nargs="*", default=None)
+ap.add_argument("--gmres", action="store_true", help="also time the reference-faithful GMRES Newton at C1 (tens of seconds)")
 args = ap.parse_args()
 want = lambda c: args.only is None or c in args.only
 
@@ -90,6 +91,10 @@ if want("C1"):   # YAML default grid: 200x7, T=150 — steady state, Jacobian an
         NewtonRaphsonHANK(x0, J, prob, solver=sv, verbose=False)
         t0 = time.perf_counter(); x, st = NewtonRaphsonHANK(x0, J, prob, solver=sv, verbose=False)
         res[sv] = {"ms": round(1e3 * (time.perf_counter() - t0), 2), "outer": st["outer"], "jvps": st["jvps"], "inner": st["inner"]}
+    if args.gmres:   # reference-faithful inner solver: restarted GMRES(20), maxiter = n per call
+        t0 = time.perf_counter(); xg, stg = NewtonRaphsonHANK(x0, J, prob, solver="gmres", verbose=False)
+        res["gmres"] = {"ms": round(1e3 * (time.perf_counter() - t0), 1), "outer": stg["outer"], "jvps": stg["jvps"],
+                        "gmres_iters": stg["gmres_iters"], "max_abs_diff_vs_lu": float(np.max(np.abs(xg - x)))}
     print(json.dumps({"config": "C1 KS 200x7 T=150 (YAML default) via the host API", "steady_state": {"s": round(t_ss, 2), **info, "r": ss.vars["r"], "KS": ss.vars["KS"]},
                       "jacobian_build_ms": round(1e3 * t_J, 2), "newton": res, "residual_norm": float(np.linalg.norm(prob.fullFunction(x)))}))
     prob.blk.close()
