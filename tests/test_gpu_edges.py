@@ -1,0 +1,127 @@
+"""GPU edge cases and full-size property tests.
+
+Edge cases against the oracle: grid sizes on the padding boundaries (n_a == LDA), the minimal horizon T = 2,
+a binding non-zero borrowing constraint, lane counts that do not divide the lanes per CTA, multi-wave lane
+counts, every compiled n_e.  Full BASELINE sizes (500x7 T=300, 2000x11 T=500) through size-independent
+properties: linearity of the JVP, agreement with central finite differences, Jacobian column == unit-seed JVP,
+mass conservation, Newton residual."""
+import os
+
+import numpy as np
+import pytest
+
+from common import synthetic, make_oracle, make_block, close, maxerr, model_inputs
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _compare(n_a, n_e, T, K, gamma=2.0, borrow_cons=0.0, amax=200.0):
+    s = synthetic(n_a, n_e, T, K, gamma)
+    if borrow_cons:
+        s["m"]["borrow_cons"] = borrow_cons
+    orc = make_oracle(s["m"], T)
+    pol_o, dpol_o, v1_o, _ = orc.backward(s["vT"], s["r"], s["w"], s["dr"] if K else None, s["dw"] if K else None)
+    KD_o, dKD_o = orc.forward(s["D0"], pol_o, dpol_o if K else None)
+    blk = make_block(s["m"], T)
+    blk.set_terminal(s["vT"]); blk.set_initial_dist(s["D0"])
+    KD, dKD = blk.block(s["r"], s["w"], s["dr"] if K else None, s["dw"] if K else None)
+    assert close(blk.policies(0), pol_o) and close(blk.value_first(), v1_o) and close(KD, KD_o), maxerr(KD, KD_o)
+    if K:
+        assert close(dKD, dKD_o), maxerr(dKD, dKD_o)
+        for l in (0, K // 2, K - 1):
+            dp = blk.policies(l + 1)
+            assert close(dp, dpol_o[l]), (l, maxerr(dp, dpol_o[l]))
+    blk.close()
+    return pol_o
+
+
+@pytest.mark.parametrize("n_a", [2, 33, 256, 257, 512, 1024, 2048])
+def test_grid_sizes_on_padding_boundaries(n_a):
+    _compare(n_a, 3, 5, 3)
+
+
+def test_minimal_horizon():
+    _compare(200, 7, 2, 5)          # P = 1: one EGM step, one lottery step
+
+
+def test_binding_nonzero_borrowing_constraint():
+    pol = _compare(300, 7, 10, 4, borrow_cons=0.2)
+    assert np.mean(pol == 0.2) > 0.05    # the constraint binds on part of the grid
+
+
+@pytest.mark.parametrize("n_a,n_e,K", [(120, 3, 301), (500, 7, 7), (500, 7, 160), (500, 7, 310), (500, 7, 893), (1000, 7, 149), (1000, 7, 445)])
+def test_lane_counts_and_shapes(n_a, n_e, K):
+    """1-, 2-, 4-, 6- (and 3-) lane CTAs, partially filled last CTA, more than one wave."""
+    _compare(n_a, n_e, 6, K)
+
+
+@pytest.mark.parametrize("gamma", [1.0, 1.5, 2.0, 3.0, 4.5])
+def test_risk_aversion_values(gamma):
+    _compare(150, 7, 8, 2, gamma=gamma)
+
+
+# ---------------------------------------------------------------- full-size properties
+def _ks_block(fixture):
+    g = np.load(os.path.join(ROOT, "tests", "golden", fixture))
+    T = int(g["T"]); P = T - 1
+    m = dict(grid=g["grid"], z=g["z"], Pi=g["Pi"], beta=float(g["beta"]), gamma=float(g["gamma"]), borrow_cons=float(g["borrow_cons"]))
+    blk = make_block(m, T)
+    blk.set_terminal(g["ss_value"]); blk.set_initial_dist(g["ss_D"])
+    blk.ks_configure(float(g["alpha"]), float(g["delta"]), float(g["ss_vars"][1]))
+    x0 = np.tile(g["ss_vars"][:4], P); Z = 1.0 + 0.8 ** np.arange(1, P + 1)
+    return blk, x0, Z, P
+
+
+def test_full_size_properties_500x7_T300():
+    blk, x0, Z, P = _ks_block("ss_500x7_T300.npz")
+    n = 4 * P
+    rng = np.random.default_rng(3)
+    F = blk.linearize(x0, Z)
+    for t in (1, P // 2, P):
+        D = blk.dist(t)
+        assert abs(D.sum() - 1.0) < 1e-12 and D.min() >= 0.0          # mass conservation, positivity
+    U = rng.standard_normal((2, n))
+    a, b = 0.7, -1.3
+    JV = blk.jvp(np.vstack([U, (a * U[0] + b * U[1])[None]]))
+    assert close(JV[2], a * JV[0] + b * JV[1], rtol=1e-9, atol=1e-11)   # linearity
+    v = U[0] / np.linalg.norm(U[0]); h = 1e-6
+    fd = (blk.linearize(x0 + h * v, Z) - blk.linearize(x0 - h * v, Z)) / (2 * h)
+    blk.linearize(x0, Z)
+    jv = blk.jvp(v)[0]
+    assert np.linalg.norm(fd - jv) / np.linalg.norm(jv) < 1e-6          # JVP vs central differences
+    cols = [3, 4, n // 2 + 2, n - 1, n]                                 # 1-based columns
+    E = np.zeros((len(cols), n)); E[np.arange(len(cols)), np.array(cols) - 1] = 1.0
+    Jc = np.stack([blk.jacobian_columns(c, c + 1)[:, 0] for c in cols])
+    assert close(Jc, blk.jvp(E))                                        # unit-seed columns == generic JVPs
+    # Y and KS columns have no household term: only the direct residual entries
+    jy = blk.jacobian_columns(1, 2)[:, 0]
+    assert jy[0] == 1.0 and np.count_nonzero(jy) == 1
+    # Newton path converges on the full-size problem (batched mode; the sequential mode is covered at small T)
+    blk.linearize(x0, np.ones(P))
+    Jbar = blk.jacobian_columns(1, n + 1)
+    x, st = blk.newton_solve(Jbar, x0, Z, solver="lu_batched")
+    assert st["outer"] == 5 and st["inner"] == [38, 48, 47, 38, 22]     # SURVEY Appendix C probe counts
+    assert np.linalg.norm(blk.linearize(x, Z)) < 1e-8
+    blk.close()
+
+
+def test_full_size_properties_2000x11_T500():
+    s = synthetic(2000, 11, 500, 2)
+    blk = make_block(s["m"], 500)
+    blk.set_terminal(s["vT"]); blk.set_initial_dist(s["D0"])
+    KD, dKD = blk.block(s["r"], s["w"], s["dr"], s["dw"])
+    for t in (1, 250, 499):
+        assert abs(blk.dist(t).sum() - 1.0) < 1e-12
+    pol = blk.policy(250)
+    assert np.all(np.diff(pol, axis=1) >= 0) and pol.min() >= 0.0 and pol.max() <= s["m"]["grid"][-1]   # monotone, in range
+    h = 1e-6
+    KDp, _ = blk.block(s["r"] + h * s["dr"][0], s["w"] + h * s["dw"][0])
+    KDm, _ = blk.block(s["r"] - h * s["dr"][0], s["w"] - h * s["dw"][0])
+    fd = (KDp - KDm) / (2 * h)
+    assert np.linalg.norm(fd - dKD[0]) / np.linalg.norm(fd) < 1e-6
+    # linearity across lanes: lane 3 = 2*lane 1 - lane 2
+    dr3 = np.vstack([s["dr"], 2 * s["dr"][0] - s["dr"][1]]); dw3 = np.vstack([s["dw"], 2 * s["dw"][0] - s["dw"][1]])
+    _, d3 = blk.block(s["r"], s["w"], dr3, dw3)
+    assert close(d3[2], 2 * d3[0] - d3[1], rtol=1e-9, atol=1e-11)
+    blk.close()
