@@ -147,9 +147,11 @@ __global__ void k_lottery(const double* __restrict__ grid, int n_a, int G, const
 #define NE_DISPATCH(c, CALL)                                                              \
   switch ((c)->n_e) {                                                                     \
     case 3: return Sweeps<3>::CALL;                                                       \
+    case 5: return Sweeps<5>::CALL;                                                       \
     case 7: return Sweeps<7>::CALL;                                                       \
+    case 9: return Sweeps<9>::CALL;                                                       \
     case 11: return Sweeps<11>::CALL;                                                     \
-    default: return set_error(c, HANK_ERR_ARG, "n_e must be one of 3, 7, 11 in this build"); \
+    default: return set_error(c, HANK_ERR_ARG, "n_e must be one of 3, 5, 7, 9, 11 in this build"); \
   }
 static int sw_backward_primal(hank_ctx* c, int P, const double* vT, const double* r, const double* w) {
   NE_DISPATCH(c, backward_primal(c, P, vT, r, w));
@@ -310,7 +312,8 @@ int hank_ctx_create(hank_ctx** out, int device, int n_a, int n_e, int T, const d
     for (int e2 = 0; e2 < n_e; ++e2) c->h_Pi[(size_t)e * n_e + e2] = Pi[e + (size_t)n_e * e2];
   for (int a = 1; a < n_a; ++a)
     if (!(grid[a] > grid[a - 1])) return set_error(c, HANK_ERR_ARG, "grid must be strictly increasing");
-  if (n_e != 3 && n_e != 7 && n_e != 11) return set_error(c, HANK_ERR_ARG, "n_e must be one of 3, 7, 11 in this build");
+  if (n_e != 3 && n_e != 5 && n_e != 7 && n_e != 9 && n_e != 11)
+    return set_error(c, HANK_ERR_ARG, "n_e must be one of 3, 5, 7, 9, 11 in this build");
   Shape s;
   if (!pick_shape(n_a, &s)) return set_error(c, HANK_ERR_ARG, "n_a > 2048 is not supported in this build");
   c->lda = s.NT * s.R; c->Gp = n_e * c->lda;

@@ -1,0 +1,3 @@
+// Instantiates the sweep launchers for n_e = 9 (see hank_launch.cuh).
+#include "hank_launch.cuh"
+namespace hank { template struct Sweeps<9>; }

@@ -56,6 +56,11 @@ def test_lane_counts_and_shapes(n_a, n_e, K):
     _compare(n_a, n_e, 6, K)
 
 
+@pytest.mark.parametrize("n_e", [3, 5, 7, 9, 11])
+def test_every_compiled_income_grid(n_e):
+    _compare(200, n_e, 6, 5)
+
+
 @pytest.mark.parametrize("gamma", [1.0, 1.5, 2.0, 3.0, 4.5])
 def test_risk_aversion_values(gamma):
     _compare(150, 7, 8, 2, gamma=gamma)
