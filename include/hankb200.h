@@ -99,7 +99,9 @@ int hank_backward(hank_ctx* ctx, const double* r, const double* w /* P */, int K
 /* ForwardIteration(policy_seqs, model, ss_initial) — ForwardIteration.jl:253-311, on the
  * policies left on the device by hank_backward.  KD: P, dKD: P x K.                          */
 int hank_forward(hank_ctx* ctx, double* KD, double* dKD);
-/* Same, but for caller-supplied policies (P matrices, G x P) and tangents (G x P x K).       */
+/* Same, but for caller-supplied policies (P matrices, G x P) and tangents (G x P x K).  A policy
+ * that is not monotone in a is handled by a scatter (atomic) sweep when K = 0 and rejected with
+ * HANK_ERR_NONMONOTONE when tangent lanes are requested.                                       */
 int hank_forward_policies(hank_ctx* ctx, const double* policy, int K, const double* dpolicy,
                           double* KD, double* dKD);
 /* hank_backward followed by hank_forward.                                                   */

@@ -143,6 +143,56 @@ __global__ void k_lottery(const double* __restrict__ grid, int n_a, int G, const
   if (om_out) om_out[i] = om;
 }
 
+// Scatter formulation of the forward sweep for policies that are NOT monotone in a (the reference's
+// make_endogenous_transition accepts any policy, ForwardIteration.jl:37-78).  One CTA, FP64 global atomics,
+// runtime n_e; correctness path only (the gather kernels reject such policies).  D, tmp, Dn: [n_e][lda].
+__global__ void __launch_bounds__(1024, 1)
+k_forward_scatter(int n_a, int n_e, int lda, int P, const double* __restrict__ grid, const double* __restrict__ Pi,
+                  const double* __restrict__ D0, const double* __restrict__ pol, int fw_chunk_bytes, unsigned char* fw,
+                  int* mbr, double* scratch, double* KD) {
+  __shared__ double red[33];
+  const int Gp = n_e * lda, tid = threadIdx.x, NT = blockDim.x;
+  double* D = scratch; double* tmp = scratch + Gp; double* Dn = scratch + 2 * Gp;
+  for (int i = tid; i < Gp; i += NT) D[i] = D0[i];
+  __syncthreads();
+  for (int t = 0; t < P; ++t) {
+    for (int i = tid; i < Gp; i += NT) tmp[i] = 0.0;
+    __syncthreads();
+    for (int i = tid; i < Gp; i += NT) {
+      const int e = i / lda, a = i - e * lda;
+      if (a >= n_a) continue;
+      const double p = pol[(size_t)t * Gp + i], d = D[i];
+      const int m = lower_bound(grid, n_a, p) + 1;
+      mbr[(size_t)t * Gp + i] = m;
+      if (m == 1) atomicAdd(&tmp[e * lda], d);
+      else if (m > n_a) atomicAdd(&tmp[e * lda + n_a - 1], d);
+      else {
+        const double om = (p - grid[m - 2]) / (grid[m - 1] - grid[m - 2]);
+        atomicAdd(&tmp[e * lda + m - 2], (1.0 - om) * d);
+        atomicAdd(&tmp[e * lda + m - 1], om * d);
+      }
+    }
+    __syncthreads();
+    double kacc = 0.0;
+    for (int i = tid; i < Gp; i += NT) {
+      const int e2 = i / lda, a = i - e2 * lda;
+      if (a >= n_a) continue;
+      double d = 0.0;
+      for (int e = 0; e < n_e; ++e) d += Pi[e * n_e + e2] * tmp[e * lda + a];
+      Dn[i] = d;
+      reinterpret_cast<double*>(fw + ((size_t)t * n_e + e2) * fw_chunk_bytes)[FW_D * lda + a] = d;
+      kacc += pol[(size_t)t * Gp + i] * d;
+    }
+    kacc = warp_sum(kacc);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = kacc;
+    __syncthreads();
+    if (tid == 0) { double s = 0.0; for (int w = 0; w < NT / 32; ++w) s += red[w]; KD[t] = s; }
+    double* sw = D; D = Dn; Dn = sw;
+    __syncthreads();
+  }
+}
+
 // ---- n_e dispatch ----------------------------------------------------------------------
 #define NE_DISPATCH(c, CALL)                                                              \
   switch ((c)->n_e) {                                                                     \
@@ -336,6 +386,8 @@ int hank_ctx_create(hank_ctx** out, int device, int n_a, int n_e, int T, const d
   const size_t PG = (size_t)c->P * c->Gp;
   RC(dalloc(c, &c->d_grid, n_a));
   CK(cudaMemcpy(c->d_grid, grid, n_a * sizeof(double), cudaMemcpyHostToDevice));
+  RC(dalloc(c, &c->d_Pi, (size_t)n_e * n_e));
+  CK(cudaMemcpy(c->d_Pi, c->h_Pi.data(), (size_t)n_e * n_e * sizeof(double), cudaMemcpyHostToDevice));
   RC(dalloc(c, &c->d_valueT, c->Gp)); RC(dalloc(c, &c->d_D0, c->Gp));
   CK(cudaMemset(c->d_valueT, 0, c->Gp * sizeof(double))); CK(cudaMemset(c->d_D0, 0, c->Gp * sizeof(double)));
   RC(dalloc(c, &c->d_r, c->P)); RC(dalloc(c, &c->d_w, c->P));
@@ -365,7 +417,7 @@ void hank_ctx_destroy(hank_ctx* c) {
   if (c->ev_fp) cudaEventDestroy(c->ev_fp);
   hank_comm_destroy(c);
   Tape& tp = c->tape;
-  dfree(c->d_grid); dfree(c->d_valueT); dfree(c->d_D0); dfree(c->d_r); dfree(c->d_w);
+  dfree(c->d_grid); dfree(c->d_valueT); dfree(c->d_D0); dfree(c->d_Pi); dfree(c->d_scatter); dfree(c->d_r); dfree(c->d_w);
   dfree(tp.pol); dfree(tp.bw); dfree(tp.rho); dfree(tp.fw); dfree(tp.mbr);
   dfree(tp.value_first);
   dfree(c->d_dr); dfree(c->d_dw); dfree(c->d_dpol); dfree(c->d_dvalT); dfree(c->d_dvalue_first);
@@ -505,6 +557,18 @@ int hank_forward(hank_ctx* c, double* KD, double* dKD) {
   if (!c->have_backward) return set_error(c, HANK_ERR_STATE, "hank_forward needs a preceding hank_backward");
   const int K = c->K_last, P = c->P;
   RC(forward_dev(c, c->tape.pol, K, c->d_dpol, c->d_KD, c->d_dKD));
+  int rc = check_status(c);
+  if (rc == HANK_ERR_NONMONOTONE && K == 0) {
+    // a policy that is not monotone in a: redo the sweep with the scatter (atomic) lottery
+    if (!c->d_scatter) RC(dalloc(c, &c->d_scatter, (size_t)3 * c->Gp));
+    k_forward_scatter<<<1, 1024, 0, c->stream>>>(c->n_a, c->n_e, c->lda, P, c->d_grid, c->d_Pi, c->d_D0, c->tape.pol,
+                                                 (int)fw_chunk(c), c->tape.fw, c->tape.mbr, c->d_scatter, c->d_KD);
+    c->launches++;
+    CK(cudaGetLastError());
+    c->have_forward = true;
+    rc = check_status(c);
+  }
+  if (rc) return rc;
   CK(cudaMemcpyAsync(KD, c->d_KD, P * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   if (K > 0 && dKD) CK(cudaMemcpyAsync(dKD, c->d_dKD, (size_t)K * P * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   return check_status(c);
@@ -522,6 +586,18 @@ int hank_forward_policies(hank_ctx* c, const double* policy, int K, const double
                          (size_t)c->n_a * 8, (size_t)c->n_a * 8, (size_t)P * c->n_e, cudaMemcpyDefault, c->stream));
   c->have_backward = false; c->linearized = false; c->K_last = K;
   RC(forward_dev(c, c->tape.pol, K, c->d_dpol, c->d_KD, c->d_dKD));
+  int rc = check_status(c);
+  if (rc == HANK_ERR_NONMONOTONE && K == 0) {
+    // a policy that is not monotone in a: redo the sweep with the scatter (atomic) lottery
+    if (!c->d_scatter) RC(dalloc(c, &c->d_scatter, (size_t)3 * c->Gp));
+    k_forward_scatter<<<1, 1024, 0, c->stream>>>(c->n_a, c->n_e, c->lda, P, c->d_grid, c->d_Pi, c->d_D0, c->tape.pol,
+                                                 (int)fw_chunk(c), c->tape.fw, c->tape.mbr, c->d_scatter, c->d_KD);
+    c->launches++;
+    CK(cudaGetLastError());
+    c->have_forward = true;
+    rc = check_status(c);
+  }
+  if (rc) return rc;
   CK(cudaMemcpyAsync(KD, c->d_KD, P * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   if (K > 0 && dKD) CK(cudaMemcpyAsync(dKD, c->d_dKD, (size_t)K * P * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   return check_status(c);

@@ -22,6 +22,7 @@ struct hank_ctx {
   int smem_max = 0, sm_count = 0;
 
   double *d_grid = nullptr, *d_valueT = nullptr, *d_D0 = nullptr;
+  double *d_Pi = nullptr, *d_scatter = nullptr;   // Π row-major; 3 grids of scratch for the scatter lottery
   double *d_r = nullptr, *d_w = nullptr;
   hank::Tape tape{};
   bool have_terminal = false, have_D0 = false, have_backward = false, have_forward = false;

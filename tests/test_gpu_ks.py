@@ -112,10 +112,17 @@ def test_error_semantics_gpu():
     assert close(val, vo) and close(pol, po)
     with pytest.raises(HankError):
         blk.forward()          # call order: forward before backward
-    pol3 = np.tile(pol[None], (3, 1, 1)); pol3[1, 0, 5] = 150.0   # non-monotone policy
+    # a policy that is not monotone in a (the reference accepts any policy): scatter path for the primal,
+    # rejected when tangent lanes ride along
+    pol3 = np.tile(pol[None], (3, 1, 1)); pol3[1, 0, 5] = 150.0; pol3[2, 1, 40] = 0.0
     blk.set_initial_dist(s["D0"])
+    KD3, _ = blk.forward_policies(pol3)
+    orc3 = make_oracle(s["m"], 4)
+    KD3o, _, Dp3o, _ = orc3.forward(s["D0"], pol3, want_path=True)
+    assert close(KD3, KD3o), maxerr(KD3, KD3o)
+    assert close(blk.dist(3), Dp3o[2]) and np.array_equal(blk.brackets(2), orc3.lottery(pol3[1])[0])
     with pytest.raises(HankError) as ei:
-        blk.forward_policies(pol3)
+        blk.forward_policies(pol3, np.zeros((1,) + pol3.shape))
     assert ei.value.code == 6
     blk.close()
 
