@@ -510,6 +510,7 @@ static int backward_dev(hank_ctx* c, const double* r, const double* w, int K, co
   return HANK_OK;
 }
 static int forward_dev(hank_ctx* c, const double* pol, int K, const double* dpol, double* KD, double* dKD) {
+  RC(join_side(c));  // a forward primal sweep still in flight on the side stream writes the same tape
   if (!c->have_D0) return set_error(c, HANK_ERR_STATE, "hank_set_initial_dist has not been called");
   RC(sw_forward_primal(c, c->P, c->d_D0, pol, KD));
   if (c->fp_cluster) {  // the cluster kernel leaves per-column, per-warp partials of <p_t, D_t>

@@ -174,7 +174,7 @@ static int bt_launch(hank_ctx* c, int P, int K, const double* dr, const double* 
   const Consts<NE> M = make_consts<NE>(c, P);
   const int grid = (K + L - 1) / L;
   constexpr int LDA = NT * R;
-  if (LDA <= 1024 && !c->no_tma) {  // TMA-staged tape ring (hank_tangent_tma.cuh)
+  if constexpr (LDA <= 1024) if (!c->no_tma) {  // TMA-staged tape ring (hank_tangent_tma.cuh)
     const size_t slot = bw_chunk_bytes<LDA>();
     const size_t fixed = (size_t)2 * L * LDA * 8 + (size_t)2 * L * P * 8 + (size_t)((P + 1) & ~1) * 8 + 16 * 8 + 128;
     int S = fixed < (size_t)c->smem_max ? (int)(((size_t)c->smem_max - fixed) / slot) : 0;
@@ -192,7 +192,7 @@ static int ft_launch(hank_ctx* c, int P, int K, const double* dpol, double* dkdp
   const Consts<NE> M = make_consts<NE>(c, P);
   const int grid = (K + L - 1) / L;
   constexpr int LDA = NT * R;
-  if (LDA <= 1024 && !c->no_tma) {
+  if constexpr (LDA <= 1024) if (!c->no_tma) {
     const size_t slot = fw_chunk_bytes<LDA>() + (size_t)L * LDA * 8;
     const size_t fixed = (size_t)4 * L * LDA * 8 + 16 * 8 + 128;
     int S = fixed < (size_t)c->smem_max ? (int)(((size_t)c->smem_max - fixed) / slot) : 0;
