@@ -276,9 +276,11 @@ def main():
             traffic = per_lane * K if per_lane else None
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+    tma = fx["n_a"] <= 1024 and os.environ.get("HANK_NO_TMA") != "1"
+    roofline = {"bound": "hbm", "kernel": "k_" + dom + ("_tma" if tma else ""), "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
                 "kernel_ms_per_launch": per,
+                "frac_by_kernel": {k: alg / (per[k] * 1e-3) / 1e9 / peak for k in ("backward_tangent", "forward_tangent")},
                 "sweep_pair_GBps": 2 * alg / ((per["backward_tangent"] + per["forward_tangent"]) * 1e-3) / 1e9}
 
     out = {
