@@ -147,6 +147,8 @@ __device__ __forceinline__ void gather_row(const double* __restrict__ xb, const 
   for (int l = 0; l < L; ++l) acc[l] = 0.0;
 #pragma unroll
   for (int d = 0; d < U; ++d) {
+    // most rows have one source per range: the second round is skipped by warps in which no row needs it
+    if (d > 0 && !__any_sync(0xffffffffu, (d < n1) | (d < n2))) break;
     if (d < n1) {
 #pragma unroll
       for (int l = 0; l < L; ++l) acc[l] += xb[l * LDA + s0 + d];
