@@ -99,6 +99,29 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// Sums of L per-thread values over the warp with L-1 + 5-log2(L) shuffles instead of 5 L: each
+// halving step keeps half of the values and hands the other half to the partner lane.  The total
+// of value l ends up in every lane whose top log2(L) lane-index bits spell l (lane (l*32)/L first).
+template <int L>
+__device__ __forceinline__ double warp_sum_multi(double (&v)[L], int lane) {
+  static_assert(L == 1 || L == 2 || L == 4, "power-of-two lane counts only");
+  int o = 16;
+#pragma unroll
+  for (int h = L / 2; h >= 1; h >>= 1, o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const double send = up ? v[i] : v[i + h];
+      const double keep = up ? v[i + h] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  double r = v[0];
+#pragma unroll
+  for (; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  return r;
+}
+
 // searchsortedfirst on a sorted shared/global array: number of elements < x (0-based result).
 __device__ __forceinline__ int lower_bound(const double* __restrict__ v, int n, double x) {
   int lo = 0, hi = n;

@@ -269,16 +269,20 @@ k_forward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int Kp, int S, c
       int s0[R], s1[R], s2[R];
 #pragma unroll
       for (int j = 0; j < R; ++j) {
+        // all shared-memory loads of the row first: the stores below may alias them as far as the
+        // compiler can tell, so loads written after a store would wait for it
+        double pd[L];
+#pragma unroll
+        for (int l = 0; l < L; ++l) pd[l] = sl[PD_OFF + l * LDA + j * NT];
         const double om = sl[FW_OM * LDA + j * NT], dco = sl[FW_DCO * LDA + j * NT], Dn = sl[FW_D * LDA + j * NT];
         pv[j][e] = sl[FW_P * LDA + j * NT];
         s0[j] = sst[j * NT]; s1[j] = sst[j * NT + 1]; s2[j] = sst[j * NT + 2];
 #pragma unroll
         for (int l = 0; l < L; ++l) {
-          const double pd = sl[PD_OFF + l * LDA + j * NT];
-          const double xd = fma(om, Dd[l][j][e], dco * pd);
+          const double xd = fma(om, Dd[l][j][e], dco * pd[l]);
           xb[l * LDA + j * NT + tid] = xd;
           yb[l * LDA + j * NT + tid] = Dd[l][j][e] - xd;
-          kacc[l] = fma(pd, Dn, kacc[l]);
+          kacc[l] = fma(pd[l], Dn, kacc[l]);
         }
       }
       __syncthreads();
@@ -316,10 +320,16 @@ k_forward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int Kp, int S, c
         for (int e2 = 0; e2 < NE; ++e2) { Dd[l][j][e2] = d[e2]; kacc[l] = fma(pv[j][e2], d[e2], kacc[l]); }
       }
     }
+    if constexpr (L == 1 || L == 2 || L == 4) {
+      const double s = warp_sum_multi<L>(kacc, lane);
+      const int l = lane / (32 / L);
+      if ((lane & (32 / L - 1)) == 0 && lane0 + l < K) dkdpart[((size_t)(lane0 + l) * P + t) * NW + warp] = s;
+    } else {
 #pragma unroll
-    for (int l = 0; l < L; ++l) {
-      const double s = warp_sum(kacc[l]);
-      if (lane == 0 && lane0 + l < K) dkdpart[((size_t)(lane0 + l) * P + t) * NW + warp] = s;
+      for (int l = 0; l < L; ++l) {
+        const double s = warp_sum(kacc[l]);
+        if (lane == 0 && lane0 + l < K) dkdpart[((size_t)(lane0 + l) * P + t) * NW + warp] = s;
+      }
     }
   }
   if (dD_last) {
