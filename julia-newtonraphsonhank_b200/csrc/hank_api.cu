@@ -370,6 +370,7 @@ int hank_ctx_create(hank_ctx** out, int device, int n_a, int n_e, int T, const d
   { const char* nt = getenv("HANK_NO_TMA"); c->no_tma = nt && nt[0] == '1'; }
   { const char* nt = getenv("HANK_NO_WIDE"); c->no_wide = nt && nt[0] == '1'; }
   { const char* nt = getenv("HANK_NO_CLUSTER"); c->no_cluster = nt && nt[0] == '1'; }
+  { const char* nt = getenv("HANK_NO_DSMEM"); c->no_dsmem = nt && nt[0] == '1'; }
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   {
     int lo = 0, hi = 0;

@@ -60,6 +60,7 @@ struct hank_ctx {
   bool profile = false;
   int* d_jac_idx = nullptr; int jac_idx_cap = 0;   // lane<->column maps of hank_ks_jacobian_columns
   bool no_cluster = false;       // HANK_NO_CLUSTER=1: single-CTA primal sweeps
+  bool no_dsmem = false;         // HANK_NO_DSMEM=1: cluster primal sweeps exchange through global memory
   bool fp_cluster = false;       // last forward primal ran on the cluster (per-column KD partials)
   double* d_xch = nullptr;       // [2][NE][lda] cluster exchange buffer
   bool no_wide = false;          // HANK_NO_WIDE=1: never use the 256-thread / 6-lane tangent shape

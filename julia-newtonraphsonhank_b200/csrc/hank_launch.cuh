@@ -8,6 +8,7 @@
 #include "hank_tangent.cuh"
 #include "hank_tangent_tma.cuh"
 #include "hank_primal_cluster.cuh"
+#include "hank_primal_dsmem.cuh"
 
 namespace hank {
 
@@ -73,6 +74,16 @@ static int launch_cluster(hank_ctx* c, int kind, KernelT kern, int block, size_t
 template <int NE, int R, int NT>
 static int bp_launch(hank_ctx* c, int P, const double* valueT, const double* r, const double* w) {
   const Consts<NE> M = make_consts<NE>(c, P);
+  if (!c->no_cluster && !c->no_dsmem && NE > 1 && bp_ds_smem<NE, NT * R>() <= (size_t)c->smem_max) {
+    // exchange through distributed shared memory (hank_primal_dsmem.cuh)
+    const size_t smem_d = bp_ds_smem<NE, NT * R>();
+    int rc = c->gamma == 2.0
+        ? launch_cluster<NE>(c, KIND_BP, k_backward_primal_ds<NE, R, NT, true>, NT, smem_d, "k_backward_primal_ds", M, c->tape,
+                             (const double*)c->d_grid, valueT, r, w, c->d_status)
+        : launch_cluster<NE>(c, KIND_BP, k_backward_primal_ds<NE, R, NT, false>, NT, smem_d, "k_backward_primal_ds", M, c->tape,
+                             (const double*)c->d_grid, valueT, r, w, c->d_status);
+    if (rc >= 0) return rc;
+  }
   if (!c->no_cluster && NE > 1) {
     const size_t smem_c = (size_t)2 * NT * R * sizeof(double);
     int rc = c->gamma == 2.0
@@ -103,6 +114,11 @@ template <int NE, int R, int NT, int CS>
 static int fp_launch(hank_ctx* c, int P, const double* D0, const double* pol, double* KD) {
   const Consts<NE> M = make_consts<NE>(c, P);
   constexpr int LDA = NT * R;
+  if (!c->no_cluster && !c->no_dsmem && NE > 1 && CS == NE && fp_ds_smem<NE, LDA>() <= (size_t)c->smem_max) {
+    int rc = launch_cluster<NE>(c, KIND_FP, k_forward_primal_ds<NE, R, NT>, NT, fp_ds_smem<NE, LDA>(), "k_forward_primal_ds", M,
+                                c->tape, (const double*)c->d_grid, D0, pol, c->d_kdpart, c->d_status);
+    if (rc >= 0) { c->fp_cluster = true; return rc; }
+  }
   if (!c->no_cluster && NE > 1 && CS == NE) {   // (the CS < NE instantiation only exists as the single-CTA fallback)
     const size_t smem_c = (size_t)3 * LDA * sizeof(double) + ((size_t)LDA + LDA + 4) * sizeof(int);
     int rc = launch_cluster<NE>(c, KIND_FP, k_forward_primal_cl<NE, R, NT>, NT, smem_c, "k_forward_primal_cl", M, c->tape,

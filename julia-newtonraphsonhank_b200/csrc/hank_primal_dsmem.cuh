@@ -1,0 +1,346 @@
+// hank_primal_dsmem.cuh — cluster primal sweeps whose per-period exchange goes through distributed
+// shared memory instead of global memory.
+//
+// In hank_primal_cluster.cuh every period ends in a barrier.cluster whose release fence has to wait
+// for ALL global stores of the period — the exchange column and the 60 B of tape per point — which
+// showed up as the top stall of both kernels (`membar` 4.3 / 2.5 cycles per issue,
+// profiles/r01_notes.md).  Here each thread hands its value straight to the shared memory of all
+// NE CTAs with `st.async.shared::cluster ... mbarrier::complete_tx::bytes`; a CTA waits on its own
+// mbarrier until the NE columns of the period (NE*n_a*8 bytes) have landed.  No fence, no cluster
+// barrier inside the loop, and the tape stores stay fire-and-forget.
+//
+// Two buffers / two mbarriers alternate by period.  Safety without further synchronisation:
+//  * a peer can only send period i+1 after it has received period i from every CTA, so bytes for
+//    buffer b never arrive while the previous phase of mbarrier b is still open;
+//  * a buffer is overwritten by period i+2 data only after all of this CTA's period i+1 sends,
+//    which every thread issues after its own reads of period i.
+// The per-point arithmetic is the same as in the other primal kernels, in the same order.
+#pragma once
+#include <cooperative_groups.h>
+#include "hank_kernels.cuh"
+#include "hank_tangent_tma.cuh"   // mbarrier helpers
+
+namespace hank {
+
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uint32_t remote_bar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(remote_addr), "d"(v),
+               "r"(remote_bar)
+               : "memory");
+}
+// Data written by peer CTAs: acquire at cluster scope.  Bounded like mbar_wait.
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
+template <int NE, int LDA>
+constexpr size_t bp_ds_smem() { return ((size_t)2 * NE * LDA + 3 * LDA) * 8 + 16; }
+template <int NE, int LDA>
+constexpr size_t fp_ds_smem() { return ((size_t)2 * NE * LDA + 3 * LDA) * 8 + ((size_t)LDA + LDA + 4) * 4 + 16; }
+
+// ======================================================================================
+// Backward primal sweep.  smem: xb[2][NE][LDA] ∂V/∂a of all columns | ks[2][LDA] | g[LDA] | bar[2]
+// ======================================================================================
+template <int NE, int R, int NT, bool G2>
+__global__ void __launch_bounds__(NT, 1)
+k_backward_primal_ds(const Consts<NE> M, const Tape tp, const double* __restrict__ grid,
+                     const double* __restrict__ valueT, const double* __restrict__ rpath,
+                     const double* __restrict__ wpath, int* __restrict__ status) {
+  constexpr int LDA = NT * R;
+  constexpr size_t GP = (size_t)NE * LDA;
+  extern __shared__ __align__(16) double smem_ds[];
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int e = (int)cluster.block_rank();
+  const int n_a = M.n_a, P = M.P;
+  double* xb = smem_ds;
+  double* ksb = xb + 2 * GP;
+  double* g = ksb + 2 * LDA;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(g + LDA);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int a = tid; a < n_a; a += NT) g[a] = grid[a];
+  double pi_row[NE];  // Π[e, ·]
+#pragma unroll
+  for (int e2 = 0; e2 < NE; ++e2) pi_row[e2] = M.Pi[0][0];
+#pragma unroll
+  for (int e1 = 0; e1 < NE; ++e1)
+    if (e1 == e) {
+#pragma unroll
+      for (int e2 = 0; e2 < NE; ++e2) pi_row[e2] = M.Pi[e1][e2];
+    }
+  double ze = M.z[0];
+#pragma unroll
+  for (int e1 = 0; e1 < NE; ++e1) if (e1 == e) ze = M.z[e1];
+  // this thread's slot (column e, row tid) of buffer 0 in every CTA, and every CTA's barrier 0
+  uint32_t rdst[NE], rbar[NE];
+  {
+    const uint32_t mine = smem_u32(xb + (size_t)e * LDA + tid), b0 = smem_u32(bar);
+#pragma unroll
+    for (int c = 0; c < NE; ++c) { rdst[c] = map_to_cta(mine, c); rbar[c] = map_to_cta(b0, c); }
+  }
+  cluster.sync();   // every CTA's barriers exist before anyone sends
+  const uint32_t col_bytes = (uint32_t)NE * (uint32_t)n_a * 8u;
+  double rn = rpath[P - 1], wn = wpath[P - 1];
+  double Vlast[R];
+  for (int it = 0; it < P; ++it) {
+    const int t = P - 1 - it, wb = it & 1;
+    const double r = rn, w = wn;
+    if (t > 0) { rn = rpath[t - 1]; wn = wpath[t - 1]; }
+    const double opr = 1.0 + r, rho = 1.0 / opr;
+    if (tid == 0 && e == 0) tp.rho[t] = rho;
+    if (tid == 0) mbar_expect_tx(&bar[wb], col_bytes);   // this period's incoming columns
+    double* bwf = bw_fields<LDA>(tp, NE, t, e) + tid;
+    int* bwi = bw_idx<LDA>(tp, NE, t, e) + tid;
+    double* polt = tp.pol + (size_t)t * GP + (size_t)e * LDA + tid;
+    double* ks = ksb + wb * LDA;
+    const double* vsrc = xb + (size_t)(wb ^ 1) * GP;
+    if (it > 0) mbar_wait_cluster(&bar[wb ^ 1], ((it - 1) >> 1) & 1);
+    // ---- phase 1: Euler inversion for this column
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const int a = tid + j * NT;
+      if (a < n_a) {
+        double vrow[NE];
+        if (it == 0) {
+#pragma unroll
+          for (int e2 = 0; e2 < NE; ++e2) vrow[e2] = valueT[(size_t)e2 * LDA + a];
+        } else {
+#pragma unroll
+          for (int e2 = 0; e2 < NE; ++e2) vrow[e2] = vsrc[(size_t)e2 * LDA + a];
+        }
+        double ev = 0.0;
+#pragma unroll
+        for (int e2 = 0; e2 < NE; ++e2) ev += vrow[e2] * pi_row[e2];
+        const double B = M.beta * ev;
+        if (B < 0.0) raise(status, 2, a, e, t);
+        const double c = pow_c<G2>(B, M.yexp);
+        const double S = (c - w * ze) + g[a];
+        ks[a] = rho * S;
+        bwf[BW_A1 * LDA + j * NT] = rho * (M.beta * (M.yexp * (G2 ? c * c * c : c / B)));
+        bwf[BW_KR * LDA + j * NT] = -(S * (rho / opr));
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: interpolation on the exogenous grid, clamp, marginal value
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const int a = tid + j * NT;
+      if (a < n_a) {
+        const double x = g[a];
+        if (a > 0 && !(ks[a] > ks[a - 1])) raise(status, 3, a, e, t);
+        int i; double num, den; bool interior = true;
+        const double k0 = ks[0], kl = ks[n_a - 1];
+        if (x > kl) { i = n_a - 2; den = kl - ks[i]; num = den; interior = false; }
+        else if (x < k0) { i = 0; den = ks[1] - k0; num = 0.0; interior = false; }
+        else {
+          int lb = lower_bound_fixed<LDA>(ks, n_a, x);
+          i = min(max(lb, 1), n_a - 1) - 1;
+          num = x - ks[i]; den = ks[i + 1] - ks[i];
+        }
+        const double delta = num / den;
+        const double gi = g[i], gi1 = g[i + 1];
+        const double q = (1.0 - delta) * gi + delta * gi1;
+        const bool cons = q < M.bc;
+        const double p = cons ? M.bc : q;
+        const double cg_ = (opr * x + w * ze) - p;
+        if (cg_ < 0.0 && !M.gamma_int) raise(status, 2, a, e, t);
+        double cgp, cgp1;
+        pow_v2<G2>(cg_, M.gamma, cgp, cgp1);
+        const double vnew = opr * cgp;
+        // hand ∂V/∂a(a, e) to every CTA first: it is what the next period waits for
+        const uint32_t off = (uint32_t)(wb * GP + j * NT) * 8u;
+#pragma unroll
+        for (int c = 0; c < NE; ++c) st_async_f64(rdst[c] + off, vnew, rbar[c] + 8u * wb);
+        polt[j * NT] = p;
+        bwi[j * NT] = i;
+        const bool live = interior && !cons;
+        const double dg = gi1 - gi, id = 1.0 / den, nd2 = delta * id;
+        bwf[BW_CA * LDA + j * NT] = live ? (nd2 - id) * dg : 0.0;
+        bwf[BW_CB * LDA + j * NT] = live ? -(nd2 * dg) : 0.0;
+        const double vf = opr * ((-M.gamma) * cgp1);
+        bwf[BW_VF * LDA + j * NT] = vf;
+        bwf[BW_E1 * LDA + j * NT] = cgp + vf * x;
+        Vlast[j] = vnew;
+      }
+    }
+  }
+  // the last period's columns are still in flight towards this CTA: drain before anyone exits
+  mbar_wait_cluster(&bar[(P - 1) & 1], ((P - 1) >> 1) & 1);
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const int a = tid + j * NT;
+    if (a < n_a) tp.value_first[(size_t)e * LDA + a] = Vlast[j];
+  }
+  cluster.sync();
+}
+
+// ======================================================================================
+// Forward primal sweep.  smem: xb[2][NE][LDA] post-lottery masses of all columns | X[LDA] | Y[LDA] |
+// g[LDA] | ms[LDA] (int) | st[LDA+4] (int) | bar[2].   kdpart: [P][NE*NT/32].
+// ======================================================================================
+template <int NE, int R, int NT>
+__global__ void __launch_bounds__(NT, 1)
+k_forward_primal_ds(const Consts<NE> M, const Tape tp, const double* __restrict__ grid,
+                    const double* __restrict__ D0, const double* __restrict__ pol_in,
+                    double* __restrict__ kdpart, int* __restrict__ status) {
+  constexpr int LDA = NT * R, NS = LDA + 4, NW = NT / 32;
+  constexpr size_t GP = (size_t)NE * LDA;
+  extern __shared__ __align__(16) double smem_ds[];
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int e = (int)cluster.block_rank();
+  const int n_a = M.n_a, P = M.P;
+  double* xb = smem_ds;
+  double* X = xb + 2 * GP;
+  double* Y = X + LDA;
+  double* g = Y + LDA;
+  int* ms = reinterpret_cast<int*>(g + LDA);
+  int* st = ms + LDA;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(st + NS);   // NS*4 is a multiple of 8
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int a = tid; a < n_a; a += NT) g[a] = grid[a];
+  for (int i = tid; i < NS; i += NT) st[i] = n_a;
+  double pi_col[NE];  // Π[·, e]
+#pragma unroll
+  for (int e1 = 0; e1 < NE; ++e1) pi_col[e1] = M.Pi[0][0];
+#pragma unroll
+  for (int e2 = 0; e2 < NE; ++e2)
+    if (e2 == e) {
+#pragma unroll
+      for (int e1 = 0; e1 < NE; ++e1) pi_col[e1] = M.Pi[e1][e2];
+    }
+  double D[R], pc[R], pn[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const int a = tid + j * NT;
+    D[j] = a < n_a ? D0[(size_t)e * LDA + a] : 0.0;
+    pc[j] = a < n_a ? pol_in[(size_t)e * LDA + a] : 0.0;
+    pn[j] = 0.0;
+  }
+  uint32_t rdst[NE], rbar[NE];
+  {
+    const uint32_t mine = smem_u32(xb + (size_t)e * LDA + tid), b0 = smem_u32(bar);
+#pragma unroll
+    for (int c = 0; c < NE; ++c) { rdst[c] = map_to_cta(mine, c); rbar[c] = map_to_cta(b0, c); }
+  }
+  cluster.sync();
+  const uint32_t col_bytes = (uint32_t)NE * (uint32_t)n_a * 8u;
+  for (int t = 0; t < P; ++t) {
+    const int wb = t & 1;
+    if (tid == 0) mbar_expect_tx(&bar[wb], col_bytes);
+    const double* polt = pol_in + (size_t)t * GP + (size_t)e * LDA + tid;
+    if (t + 1 < P) {
+#pragma unroll
+      for (int j = 0; j < R; ++j) pn[j] = tid + j * NT < n_a ? polt[GP + j * NT] : 0.0;
+    }
+    double* fwf = fw_fields<LDA>(tp, NE, t, e) + tid;
+    int* mbt = tp.mbr + (size_t)t * GP + (size_t)e * LDA + tid;
+    // ---- phase A: brackets and lottery masses of this column
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const int a = tid + j * NT;
+      if (a < n_a) {
+        const double p = pc[j];
+        const int m = lower_bound_fixed<LDA>(g, n_a, p) + 1;
+        double om, dco;
+        if (m == 1) { om = 1.0; dco = 0.0; }
+        else if (m > n_a) { om = 0.0; dco = 0.0; }
+        else {
+          const double dgm = g[m - 1] - g[m - 2];
+          om = (p - g[m - 2]) / dgm;
+          dco = D[j] / dgm;
+        }
+        X[a] = om * D[j];
+        Y[a] = (1.0 - om) * D[j];
+        ms[a] = m;
+        fwf[FW_OM * LDA + j * NT] = om;
+        fwf[FW_DCO * LDA + j * NT] = dco;
+        fwf[FW_P * LDA + j * NT] = p;
+        mbt[j * NT] = m;
+      }
+    }
+    __syncthreads();
+    // ---- phase B: source-range starts per destination row
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const int a = tid + j * NT;
+      if (a < n_a) {
+        const int hi = ms[a];
+        const int lo = a == 0 ? 0 : ms[a - 1];
+        if (hi < lo) raise(status, 6, a, e, t);
+        for (int row = lo + 1; row <= hi; ++row) st[row] = a;
+        if (a == n_a - 1)
+          for (int row = max(hi, lo) + 1; row <= n_a + 2; ++row) st[row] = n_a;
+      }
+    }
+    __syncthreads();
+    // ---- phase C: gather in ascending source order; hand this column's masses to every CTA
+    int* so = fw_start<LDA>(tp, NE, t, e);
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const int a = tid + j * NT;
+      if (a < n_a) {
+        const int s0 = st[a + 1], s1 = st[a + 2], s2 = st[a + 3];
+        double acc = 0.0;
+        for (int b = s0; b < s1; ++b) acc += X[b];
+        for (int b = s1; b < s2; ++b) acc += Y[b];
+        const uint32_t off = (uint32_t)(wb * GP + j * NT) * 8u;
+#pragma unroll
+        for (int c = 0; c < NE; ++c) st_async_f64(rdst[c] + off, acc, rbar[c] + 8u * wb);
+        so[a + 1] = s0;
+        if (a == n_a - 1) { so[a + 2] = s1; so[a + 3] = s2; }
+      }
+    }
+    __syncthreads();   // X, Y, ms, st are rewritten by the next period's phases
+    mbar_wait_cluster(&bar[wb], (t >> 1) & 1);
+    // ---- Markov mix for this column and its share of <p_t, D_t>
+    const double* tsrc = xb + (size_t)wb * GP;
+    double kacc = 0.0;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const int a = tid + j * NT;
+      if (a < n_a) {
+        double d = 0.0;
+#pragma unroll
+        for (int e1 = 0; e1 < NE; ++e1) d += pi_col[e1] * tsrc[(size_t)e1 * LDA + a];
+        D[j] = d;
+        fwf[FW_D * LDA + j * NT] = d;
+        kacc += pc[j] * d;
+      }
+    }
+    kacc = warp_sum(kacc);
+    if (lane == 0) kdpart[((size_t)t * NE + e) * NW + warp] = kacc;
+#pragma unroll
+    for (int j = 0; j < R; ++j) pc[j] = pn[j];
+  }
+  cluster.sync();   // no CTA leaves while a peer may still be writing into it
+}
+
+}  // namespace hank

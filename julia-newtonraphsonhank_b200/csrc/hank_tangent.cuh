@@ -143,19 +143,35 @@ template <int L, int LDA, int U>
 __device__ __forceinline__ void gather_row(const double* __restrict__ xb, const double* __restrict__ yb, int s0,
                                            int s1, int s2, int lane, double (&acc)[L]) {
   const int n1 = s1 - s0, n2 = s2 - s1;
+  // Most rows have one source per range: the second round is skipped by warps in which no row needs it.
+  if constexpr (L > 4) {
+    // wide shapes: absent sources load as zeros and the adds form a short tree (measured 15 % faster
+    // at L = 6, 2 % slower at L = 4 than the predicated chain below)
 #pragma unroll
-  for (int l = 0; l < L; ++l) acc[l] = 0.0;
+    for (int d = 0; d < U; ++d) {
+      if (d > 0 && !__any_sync(0xffffffffu, (d < n1) | (d < n2))) break;
+      double x[L], y[L];
 #pragma unroll
-  for (int d = 0; d < U; ++d) {
-    // most rows have one source per range: the second round is skipped by warps in which no row needs it
-    if (d > 0 && !__any_sync(0xffffffffu, (d < n1) | (d < n2))) break;
-    if (d < n1) {
+      for (int l = 0; l < L; ++l) x[l] = d < n1 ? xb[l * LDA + s0 + d] : 0.0;
 #pragma unroll
-      for (int l = 0; l < L; ++l) acc[l] += xb[l * LDA + s0 + d];
+      for (int l = 0; l < L; ++l) y[l] = d < n2 ? yb[l * LDA + s1 + d] : 0.0;
+#pragma unroll
+      for (int l = 0; l < L; ++l) acc[l] = d == 0 ? x[l] + y[l] : acc[l] + (x[l] + y[l]);
     }
-    if (d < n2) {
+  } else {
 #pragma unroll
-      for (int l = 0; l < L; ++l) acc[l] += yb[l * LDA + s1 + d];
+    for (int l = 0; l < L; ++l) acc[l] = 0.0;
+#pragma unroll
+    for (int d = 0; d < U; ++d) {
+      if (d > 0 && !__any_sync(0xffffffffu, (d < n1) | (d < n2))) break;
+      if (d < n1) {
+#pragma unroll
+        for (int l = 0; l < L; ++l) acc[l] += xb[l * LDA + s0 + d];
+      }
+      if (d < n2) {
+#pragma unroll
+        for (int l = 0; l < L; ++l) acc[l] += yb[l * LDA + s1 + d];
+      }
     }
   }
   // a few more sources: finish in this thread; long ranges: the whole warp, one row at a time
