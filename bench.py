@@ -63,7 +63,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(index)], stdout=subprocess.PIPE, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -79,9 +79,14 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for ts, line in self.rows:
-            if ts < t0 or ts > t1 + 0.2:
-                continue
+        # a sample is stamped when its line is read, i.e. up to one query (~20-50 ms) after the clocks were
+        # taken; a timed region shorter than that falls back to the samples that bracket it
+        inside = [r for r in self.rows if t0 <= r[0] <= t1 + 0.05]
+        window = "timed region"
+        if not inside:
+            inside = [r for r in self.rows if t0 - 0.3 <= r[0] <= t1 + 0.3]
+            window = "timed region +-0.3 s (region shorter than one nvidia-smi query)"
+        for ts, line in inside:
             f = [x.strip() for x in line.split(",")]
             try:
                 sm.append(float(f[0])); mx.append(float(f[1]))
@@ -92,7 +97,7 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return None
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 _W = {}
@@ -153,7 +158,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="hankb200", choices=["hankb200", "reference"])
     ap.add_argument("--workload", default="ks_500x7_T300", choices=sorted(WORKLOADS))
@@ -237,12 +242,12 @@ def main():
             ms = float(tt.item())
         return ms, t0, t1
 
+    sampler = ClockSampler(local) if rank == 0 else None   # started before the warm-up so it is already streaming
     for _ in range(max(args.warmup, 3)):
         step_dev()
     blk.sync()
     blk.profile(True); blk.kernel_times(reset=True)
     lc0 = blk.launch_count()
-    sampler = ClockSampler(local) if rank == 0 else None
     ms, t0, t1 = timed(step_dev, args.steps)
     clocks = sampler.stop(t0, t1) if sampler else None
     launches = blk.launch_count() - lc0

@@ -156,7 +156,7 @@ int Sweeps<NE>::forward_primal(hank_ctx* c, int P, const double* D0, const doubl
 // has a CTA.
 struct TangentCfg { int NT, R, L; };
 // waves(K, L) * relative cost of one wave with L lanes per CTA (measured at 500x7: a 6-lane wave
-// costs 1.47x a 4-lane wave, a 4-lane wave 1.9x a 1-lane wave; profiles/r01_notes.md)
+// costs 1.6x a 4-lane wave, a 4-lane wave 1.9x a 1-lane wave; profiles/r01_notes.md)
 static double cfg_cost(int K, int L, int sm, double wave_cost) {
   const int ctas = (K + L - 1) / L;
   return (double)((ctas + sm - 1) / sm) * wave_cost;
@@ -168,13 +168,13 @@ static TangentCfg tangent_cfg(const hank_ctx* c, int K) {
     case 512: {
       if (K <= sm) return {512, 1, 1};
       if (K <= 2 * sm) return {512, 1, 2};
-      const double c4 = cfg_cost(K, 4, sm, 1.0), c6 = cfg_cost(K, 6, sm, 1.47);
+      const double c4 = cfg_cost(K, 4, sm, 1.0), c6 = cfg_cost(K, 6, sm, 1.6);
       if (c6 < c4 && !c->no_wide) return {256, 2, 6};
       return {512, 1, 4};
     }
     case 1024: {
       if (K <= sm) return {512, 2, 1};
-      const double c2 = cfg_cost(K, 2, sm, 1.0), c3 = cfg_cost(K, 3, sm, 1.47);
+      const double c2 = cfg_cost(K, 2, sm, 1.0), c3 = cfg_cost(K, 3, sm, 1.6);
       if (c3 < c2 && !c->no_wide) return {256, 4, 3};
       return {512, 2, 2};
     }
