@@ -876,9 +876,30 @@ int hank_ks_fjvp(hank_ctx* c, const double* x, const double* Z, int K, const dou
   CK(cudaMemcpyAsync(c->d_Z, Z, P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   RC(hank_ks_linearize_dev(c, c->d_x, c->d_Z, c->d_F));
   CK(cudaStreamWaitEvent(c->stream, c->ev_v, 0));
-  RC(hank_ks_jvp_dev(c, K, c->d_V, c->d_JV));
-  CK(cudaMemcpyAsync(JV, c->d_JV, n * K * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  // A multi-wave pass is cut at CTA-wave boundaries (the first wave leaves n_e SMs to the overlapped forward
+  // primal): the columns of a finished wave travel to the host on the copy stream under the next wave.
+  const int L = std::max(1, sw_lanes_per_cta(c, K));
+  const int first = L * (c->sm_count - (c->no_overlap ? 0 : c->n_e)), wave = L * c->sm_count;
+  if (L == 4 && K > first && first > 0) {
+    for (int k0 = 0, kb = first; k0 < K; k0 += kb, kb = wave) {
+      const int kc = std::min(kb, K - k0);
+      RC(hank_ks_jvp_dev(c, kc, c->d_V + (size_t)k0 * n, c->d_JV + (size_t)k0 * n));
+      if (k0 + kc < K) {
+        CK(cudaEventRecord(c->ev_v, c->stream));
+        CK(cudaStreamWaitEvent(c->stream3, c->ev_v, 0));
+        CK(cudaMemcpyAsync(JV + (size_t)k0 * n, c->d_JV + (size_t)k0 * n, n * kc * sizeof(double), cudaMemcpyDeviceToHost,
+                           c->stream3));
+      } else {
+        CK(cudaMemcpyAsync(JV + (size_t)k0 * n, c->d_JV + (size_t)k0 * n, n * kc * sizeof(double), cudaMemcpyDeviceToHost,
+                           c->stream));
+      }
+    }
+  } else {
+    RC(hank_ks_jvp_dev(c, K, c->d_V, c->d_JV));
+    CK(cudaMemcpyAsync(JV, c->d_JV, n * K * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
   if (F) CK(cudaMemcpyAsync(F, c->d_F, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream3));
   int rc = check_status(c);
   if (rc) c->linearized = false;
   return rc;

@@ -111,6 +111,23 @@ def test_full_size_properties_500x7_T300():
     blk.close()
 
 
+def test_fjvp_multi_wave_matches_jvp():
+    """hank_ks_fjvp cuts a multi-wave pass at CTA-wave boundaries and downloads finished waves on the copy
+    stream; every column must equal the one-pass hank_ks_jvp result."""
+    blk, x0, Z, P = _ks_block("ss_500x7_T300.npz")
+    n = 4 * P
+    rng = np.random.default_rng(11)
+    for K in (570, 1190):                      # one wave + a few lanes; two waves + a few lanes
+        V = rng.standard_normal((K, n))
+        F = blk.linearize(x0, Z)
+        JV = blk.jvp(V)
+        F2, JV2 = blk.fjvp(x0, Z, V)
+        assert np.array_equal(F2, F)
+        assert close(JV2, JV), maxerr(JV2, JV)
+        assert np.all(np.isfinite(JV2))
+    blk.close()
+
+
 def test_full_size_properties_2000x11_T500():
     s = synthetic(2000, 11, 500, 2)
     blk = make_block(s["m"], 500)
