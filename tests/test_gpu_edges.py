@@ -56,6 +56,16 @@ def test_lane_counts_and_shapes(n_a, n_e, K):
     _compare(n_a, n_e, 6, K)
 
 
+@pytest.mark.parametrize("switch,n_a,K", [("HANK_NO_TMA", 500, 9), ("HANK_NO_TMA", 1000, 5), ("HANK_NO_CLUSTER", 500, 3),
+                                          ("HANK_NO_DSMEM", 500, 3), ("HANK_NO_DSMEM", 1000, 2), ("HANK_NO_WIDE", 500, 700),
+                                          ("HANK_NO_OVERLAP", 500, 5)])
+def test_fallback_kernels_agree_with_oracle(switch, n_a, K, monkeypatch):
+    """The A/B switches read at hank_ctx_create select the fallback kernels (register-prefetch tangents,
+    single-CTA and global-exchange primal sweeps, no 6-lane shape, no side stream): same parity bar."""
+    monkeypatch.setenv(switch, "1")
+    _compare(n_a, 7, 6, K)
+
+
 @pytest.mark.parametrize("n_e", [3, 5, 7, 9, 11])
 def test_every_compiled_income_grid(n_e):
     _compare(200, n_e, 6, 5)
@@ -109,6 +119,20 @@ def test_full_size_properties_500x7_T300():
     assert st["outer"] == 5 and st["inner"] == [38, 48, 47, 38, 22]     # SURVEY Appendix C probe counts
     assert np.linalg.norm(blk.linearize(x, Z)) < 1e-8
     blk.close()
+
+
+def test_side_stream_overlap_does_not_change_results(monkeypatch):
+    """hank_ks_linearize runs the forward primal sweep on a side stream under the backward tangent;
+    HANK_NO_OVERLAP=1 serialises it.  Same kernels, same results bit for bit."""
+    blk, x0, Z, P = _ks_block("ss_500x7_T300.npz")
+    V = np.random.default_rng(5).standard_normal((9, 4 * P))
+    F = blk.linearize(x0, Z); JV = blk.jvp(V)
+    blk.close()
+    monkeypatch.setenv("HANK_NO_OVERLAP", "1")
+    blk2, _, _, _ = _ks_block("ss_500x7_T300.npz")
+    F2 = blk2.linearize(x0, Z); JV2 = blk2.jvp(V)
+    blk2.close()
+    assert np.array_equal(F, F2) and np.array_equal(JV, JV2)
 
 
 def test_fjvp_multi_wave_matches_jvp():
