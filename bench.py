@@ -116,6 +116,15 @@ def _ref_worker(V):
     return float(JV.sum())
 
 
+def make_config(args, world, fx):
+    """The workload description both arms print (the reference arm times a bounded sample of it)."""
+    alg = 8.0 * fx["n_a"] * fx["n_e"] * fx["P"] * args.lanes
+    return {"workload": args.workload, "desc": WORKLOADS[args.workload]["desc"], "lanes_per_gpu_per_step": args.lanes,
+            "step": "linearise F(x) (primal sweeps) + K-lane JVP (tangent sweeps) + residual tangents"
+                    + (" + NCCL all-gather of n x K columns" if world > 1 else ""),
+            "l2": "inputs larger than L2 (policy-tangent stream %.2f GB per step vs 126 MB L2)" % (alg / 1e9)}
+
+
 def run_reference(args):
     """CPU arm: the oracle (kind "port") on the same workload, bounded sample per step.  The reference has no
     threading of its own; independent JVP directions are farmed out to one process per host core (what a user
@@ -147,8 +156,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "desc": WORKLOADS[args.workload]["desc"], "lanes_per_step": procs * Kc},
+        "config": make_config(args, args.gpus, fx),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample,
+                         "sample_lanes_per_step": procs * Kc,
                          "note": "C++ restatement of the reference CPU path (oracle/); Julia is not installed. The "
                                  "reference is single-threaded: lanes are spread over one process per host core"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -292,10 +302,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "desc": WORKLOADS[args.workload]["desc"], "lanes_per_gpu_per_step": K,
-                   "step": "linearise F(x) (primal sweeps) + K-lane JVP (tangent sweeps) + residual tangents"
-                           + (" + NCCL all-gather of n x K columns" if world > 1 else ""),
-                   "l2": "inputs larger than L2 (policy-tangent stream %.2f GB per step vs 126 MB L2)" % (alg / 1e9)},
+        "config": make_config(args, world, fx),
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(8 * (n * K + n + P)),
                 "d2h_bytes_per_step": int(8 * (n * K + n)), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
