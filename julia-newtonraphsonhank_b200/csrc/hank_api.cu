@@ -265,15 +265,15 @@ static int ensure_lanes(hank_ctx* c, int K) {
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   const size_t have = (size_t)c->Kcap * per_lane;
-  int Kmax = (int)std::min<size_t>((size_t)K, (size_t)(0.85 * (double)(free_b + have)) / per_lane - 8);
+  int Kmax = (int)std::min<size_t>((size_t)K, (size_t)(0.85 * (double)(free_b + have)) / per_lane - 16);
   if (Kmax < 1) return set_error(c, HANK_ERR_CUDA, "not enough device memory for one tangent lane");
   if (Kmax <= c->Kcap) return HANK_OK;
   dfree(c->d_dr); dfree(c->d_dw); dfree(c->d_dpol); dfree(c->d_dkdpart); dfree(c->d_dKD);
   c->Kcap = 0;
   RC(dalloc(c, &c->d_dr, (size_t)Kmax * c->P_alloc));
   RC(dalloc(c, &c->d_dw, (size_t)Kmax * c->P_alloc));
-  RC(dalloc(c, &c->d_dpol, (size_t)(Kmax + 8) * c->P_alloc * c->Gp));
-  CK(cudaMemsetAsync(c->d_dpol, 0, (size_t)(Kmax + 8) * c->P_alloc * c->Gp * sizeof(double), c->stream));
+  RC(dalloc(c, &c->d_dpol, (size_t)(Kmax + 16) * c->P_alloc * c->Gp));   // lane stride padding: up to 11 lanes
+  CK(cudaMemsetAsync(c->d_dpol, 0, (size_t)(Kmax + 16) * c->P_alloc * c->Gp * sizeof(double), c->stream));
   RC(dalloc(c, &c->d_dkdpart, (size_t)Kmax * c->P_alloc * 16));
   RC(dalloc(c, &c->d_dKD, (size_t)Kmax * c->P_alloc));
   c->Kcap = Kmax;
@@ -371,6 +371,7 @@ int hank_ctx_create(hank_ctx** out, int device, int n_a, int n_e, int T, const d
   { const char* nt = getenv("HANK_NO_WIDE"); c->no_wide = nt && nt[0] == '1'; }
   { const char* nt = getenv("HANK_NO_CLUSTER"); c->no_cluster = nt && nt[0] == '1'; }
   { const char* nt = getenv("HANK_NO_DSMEM"); c->no_dsmem = nt && nt[0] == '1'; }
+  { const char* nt = getenv("HANK_NO_SKIP"); c->no_skip = nt && nt[0] == '1'; }
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   {
     int lo = 0, hi = 0;
@@ -400,6 +401,8 @@ int hank_ctx_create(hank_ctx** out, int device, int n_a, int n_e, int T, const d
   CK(cudaMemset(tp.mbr, 0, PG * sizeof(int))); CK(cudaMemset(tp.value_first, 0, c->Gp * sizeof(double)));
   RC(dalloc(c, &c->d_kdpart, (size_t)c->P * 16 * kMaxNE)); RC(dalloc(c, &c->d_KD, c->P));
   RC(dalloc(c, &c->d_xch, (size_t)2 * c->Gp));
+  RC(dalloc(c, &c->d_zero, (size_t)kZeroBytes / sizeof(double)));
+  CK(cudaMemsetAsync(c->d_zero, 0, kZeroBytes, c->stream));
   RC(dalloc(c, &c->d_status, 4));
   CK(cudaMemset(c->d_status, 0, 4 * sizeof(int)));
   CK(cudaMallocHost((void**)&c->h_status, 4 * sizeof(int)));
@@ -422,7 +425,7 @@ void hank_ctx_destroy(hank_ctx* c) {
   dfree(tp.pol); dfree(tp.bw); dfree(tp.rho); dfree(tp.fw); dfree(tp.mbr);
   dfree(tp.value_first);
   dfree(c->d_dr); dfree(c->d_dw); dfree(c->d_dpol); dfree(c->d_dvalT); dfree(c->d_dvalue_first);
-  dfree(c->d_jac_idx); dfree(c->d_xch); dfree(c->d_kdpart); dfree(c->d_KD); dfree(c->d_dkdpart); dfree(c->d_dKD); dfree(c->d_status);
+  dfree(c->d_jac_idx); dfree(c->d_thi); dfree(c->d_zero); dfree(c->d_xch); dfree(c->d_kdpart); dfree(c->d_KD); dfree(c->d_dkdpart); dfree(c->d_dKD); dfree(c->d_status);
   dfree(c->d_x); dfree(c->d_Z); dfree(c->d_F); dfree(c->d_V); dfree(c->d_JV);
   dfree(c->d_Jinv); dfree(c->d_newton); dfree(c->d_newton_i); dfree(c->d_lu_work);
   for (auto& r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -911,7 +914,7 @@ int hank_ks_jacobian_columns_dev(hank_ctx* c, int col_begin, int col_end, double
   const int P = c->P, n = 4 * P;
   if (col_begin < 1 || col_end > n + 1 || col_end <= col_begin) return set_error(c, HANK_ERR_ARG, "bad column range");
   const int c0 = col_begin - 1, ncols = col_end - col_begin;
-  std::vector<int> lane_col, col_lane(ncols, -1);
+  std::vector<int> lane_col, col_lane(ncols, -1), chunk_cols, thi;
   for (int j = 0; j < ncols; ++j)
     if (((c0 + j) & 3) >= 2) lane_col.push_back(c0 + j);
   int Kh = (int)lane_col.size();
@@ -933,15 +936,35 @@ int hank_ks_jacobian_columns_dev(hank_ctx* c, int col_begin, int col_end, double
     const int col_hi = (k0 + kc < Kh) ? lane_col[k0 + kc] - c0 : ncols;
     const int col_lo = done_cols;
     std::fill(col_lane.begin(), col_lane.end(), -1);
-    for (int l = 0; l < kc; ++l) col_lane[lane_col[k0 + l] - c0] = l;
+    // Lanes of a chunk run latest seed first.  A unit seed at period s leaves V̇ and ṗ exactly zero after s,
+    // so each group of kThiGroup lanes carries a horizon: the backward tangent starts there, the forward
+    // tangent stages zeros beyond it, and the long CTAs are scheduled ahead of the short ones.
+    chunk_cols.assign(lane_col.begin() + k0, lane_col.begin() + k0 + kc);
+    std::reverse(chunk_cols.begin(), chunk_cols.end());
+    for (int l = 0; l < kc; ++l) col_lane[chunk_cols[l] - c0] = l;
     if (kc > 0) {
-      CK(cudaMemcpyAsync(d_lane_col, lane_col.data() + k0, kc * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+      CK(cudaMemcpyAsync(d_lane_col, chunk_cols.data(), kc * sizeof(int), cudaMemcpyHostToDevice, c->stream));
       CK(cudaMemsetAsync(c->d_dr, 0, (size_t)kc * P * sizeof(double), c->stream));
       CK(cudaMemsetAsync(c->d_dw, 0, (size_t)kc * P * sizeof(double), c->stream));
       k_unit_seeds<<<nblk(kc), 256, 0, c->stream>>>(P, kc, d_lane_col, c->d_dr, c->d_dw);
       c->launches++;
-      RC(tangent_pass(c, P, kc));
-      c->K_last = kc;
+      const int ngroups = (kc + kThiGroup - 1) / kThiGroup + 1;   // + one group of padding lanes
+      if (!c->no_skip) {
+        thi.assign(ngroups, 0);
+        for (int l = 0; l < kc; ++l) thi[l / kThiGroup] = std::max(thi[l / kThiGroup], (chunk_cols[l] >> 2) + 1);
+        if (c->thi_cap < ngroups) {
+          dfree(c->d_thi); c->thi_cap = 0;
+          RC(dalloc(c, &c->d_thi, (size_t)ngroups + 64));
+          c->thi_cap = ngroups + 64;
+        }
+        CK(cudaMemcpyAsync(c->d_thi, thi.data(), ngroups * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        c->pass_thi = c->d_thi;
+        c->pass_Kp = (kc + kThiGroup - 1) / kThiGroup * kThiGroup;
+      }
+      int rc = tangent_pass(c, P, kc);
+      c->pass_thi = nullptr; c->pass_Kp = 0;
+      RC(rc);
+      c->K_last = 0;   // policy tangents beyond the horizons were never written: not retrievable
     }
     CK(cudaMemcpyAsync(d_col_lane, col_lane.data() + col_lo, (col_hi - col_lo) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     k_ks_jac_columns<<<nblk((size_t)(col_hi - col_lo) * P), 256, 0, c->stream>>>(

@@ -65,6 +65,14 @@ struct hank_ctx {
   double* d_xch = nullptr;       // [2][NE][lda] cluster exchange buffer
   bool no_wide = false;          // HANK_NO_WIDE=1: never use the 256-thread / 6-lane tangent shape
   bool no_tma = false;           // HANK_NO_TMA=1: use the register-prefetch tangent kernels
+  bool no_skip = false;          // HANK_NO_SKIP=1: unit-seed Jacobian lanes sweep all periods
+  // Seed horizons of the pass in flight (hank_ks_jacobian_columns): lanes come in groups of kThiGroup
+  // whose seeds are zero from period pass_thi[group] on, so the backward tangent starts there and the
+  // forward tangent reads zeros instead of policy tangents beyond it.  Null for generic seeds.
+  const int* pass_thi = nullptr;
+  int pass_Kp = 0;               // lane stride of the pass (0: lanes per CTA decide)
+  int* d_thi = nullptr; int thi_cap = 0;
+  double* d_zero = nullptr;      // 32 KB of zeros: TMA source for policy tangents beyond the horizon
   struct Rec { int kind; cudaEvent_t a, b; };
   std::vector<Rec> recs;
   std::vector<cudaEvent_t> ev_pool;

@@ -99,6 +99,11 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// Seed-horizon groups: lane counts per CTA (1, 2, 3, 4, 6) all divide 12, so a horizon per 12 lanes is
+// the same for the backward and the forward kernel whatever shapes they run in.
+constexpr int kThiGroup = 12;
+constexpr int kZeroBytes = 32768;
+
 // Sums of L per-thread values over the warp with L-1 + 5-log2(L) shuffles instead of 5 L: each
 // halving step keeps half of the values and hands the other half to the partner lane.  The total
 // of value l ends up in every lane whose top log2(L) lane-index bits spell l (lane (l*32)/L first).

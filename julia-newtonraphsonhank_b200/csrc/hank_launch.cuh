@@ -189,6 +189,7 @@ static int bt_launch(hank_ctx* c, int P, int K, const double* dr, const double* 
                      double* dpol, double* dvf) {
   const Consts<NE> M = make_consts<NE>(c, P);
   const int grid = (K + L - 1) / L;
+  const int Kp = c->pass_Kp ? c->pass_Kp : grid * L;   // lane stride of the policy tangents (>= grid * L)
   constexpr int LDA = NT * R;
   if constexpr (LDA <= 1024) if (!c->no_tma) {  // TMA-staged tape ring (hank_tangent_tma.cuh)
     const size_t slot = bw_chunk_bytes<LDA>();
@@ -197,16 +198,17 @@ static int bt_launch(hank_ctx* c, int P, int K, const double* dr, const double* 
     if (S > 8) S = 8;
     if (S >= 2) {
       const size_t smem_t = fixed + (size_t)S * slot;
-      HANK_LAUNCH(KIND_BT, (k_backward_tangent_tma<NE, R, NT, L>), grid, NT, smem_t, M, c->tape, K, grid * L, S, dr, dw, dvalT, dpol, dvf);
+      HANK_LAUNCH(KIND_BT, (k_backward_tangent_tma<NE, R, NT, L>), grid, NT, smem_t, M, c->tape, K, Kp, S, c->pass_thi, dr, dw, dvalT, dpol, dvf);
     }
   }
   const size_t smem = (size_t)2 * L * LDA * sizeof(double);
-  HANK_LAUNCH(KIND_BT, (k_backward_tangent<NE, R, NT, L>), grid, NT, smem, M, c->tape, K, grid * L, dr, dw, dvalT, dpol, dvf);
+  HANK_LAUNCH(KIND_BT, (k_backward_tangent<NE, R, NT, L>), grid, NT, smem, M, c->tape, K, Kp, c->pass_thi, dr, dw, dvalT, dpol, dvf);
 }
 template <int NE, int R, int NT, int L>
 static int ft_launch(hank_ctx* c, int P, int K, const double* dpol, double* dkdpart) {
   const Consts<NE> M = make_consts<NE>(c, P);
   const int grid = (K + L - 1) / L;
+  const int Kp = c->pass_Kp ? c->pass_Kp : grid * L;
   constexpr int LDA = NT * R;
   if constexpr (LDA <= 1024) if (!c->no_tma) {
     const size_t slot = fw_chunk_bytes<LDA>() + (size_t)L * LDA * 8;
@@ -215,16 +217,16 @@ static int ft_launch(hank_ctx* c, int P, int K, const double* dpol, double* dkdp
     if (S > 8) S = 8;
     if (S >= 2) {
       const size_t smem_t = fixed + (size_t)S * slot;
-      HANK_LAUNCH(KIND_FT, (k_forward_tangent_tma<NE, R, NT, L>), grid, NT, smem_t, M, c->tape, K, grid * L, S, dpol, nullptr, dkdpart, nullptr);
+      HANK_LAUNCH(KIND_FT, (k_forward_tangent_tma<NE, R, NT, L>), grid, NT, smem_t, M, c->tape, K, Kp, S, c->pass_thi, (const double*)c->d_zero, dpol, nullptr, dkdpart, nullptr);
     }
   }
   const size_t smem = (size_t)4 * L * LDA * sizeof(double);
-  HANK_LAUNCH(KIND_FT, (k_forward_tangent<NE, R, NT, L>), grid, NT, smem, M, c->tape, K, grid * L, dpol, nullptr, dkdpart, nullptr);
+  HANK_LAUNCH(KIND_FT, (k_forward_tangent<NE, R, NT, L>), grid, NT, smem, M, c->tape, K, Kp, c->pass_thi, dpol, nullptr, dkdpart, nullptr);
 }
 
-#define TANGENT_DISPATCH(FN, ...)                                                         \
+#define TANGENT_DISPATCH(CFG, FN, ...)                                                    \
   do {                                                                                    \
-    const TangentCfg g = tangent_cfg(c, K);                                               \
+    const TangentCfg g = CFG;                                                             \
     if (g.NT == 256 && g.R == 1) {                                                        \
       if (g.L == 4) return FN<NE, 1, 256, 4>(__VA_ARGS__);                                \
       if (g.L == 2) return FN<NE, 1, 256, 2>(__VA_ARGS__);                                \
@@ -248,13 +250,19 @@ template <int NE>
 int Sweeps<NE>::backward_tangent(hank_ctx* c, int P, int K, const double* dr, const double* dw,
                                  const double* dvalT, double* dpol, double* dvf) {
   if (c->lda > 2048) return set_error(c, 1, "n_a > 2048 is not supported");
-  TANGENT_DISPATCH(bt_launch, c, P, K, dr, dw, dvalT, dpol, dvf);
+  // With seed horizons (descending over the lanes) a CTA's work shrinks with its index, so the block
+  // scheduler packs the short CTAs behind the long ones: 4-lane CTAs finish in one full-length sweep where
+  // the 6-lane shape would need one (slower) full-length wave as well.
+  TangentCfg cfg = tangent_cfg(c, K);
+  if (c->pass_thi && c->lda == 512 && cfg.L == 6) cfg = {512, 1, 4};
+  if (c->pass_thi && c->lda == 1024 && cfg.L == 3) cfg = {512, 2, 2};
+  TANGENT_DISPATCH(cfg, bt_launch, c, P, K, dr, dw, dvalT, dpol, dvf);
 }
 template <int NE>
 int Sweeps<NE>::forward_tangent(hank_ctx* c, int P, int K, const double* dpol, double* dkdpart, int* nw_out) {
   if (c->lda > 2048) return set_error(c, 1, "n_a > 2048 is not supported");
   *nw_out = tangent_cfg(c, K).NT / 32;
-  TANGENT_DISPATCH(ft_launch, c, P, K, dpol, dkdpart);
+  TANGENT_DISPATCH(tangent_cfg(c, K), ft_launch, c, P, K, dpol, dkdpart);
 }
 
 }  // namespace hank

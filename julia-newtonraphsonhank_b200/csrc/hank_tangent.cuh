@@ -21,8 +21,8 @@ namespace hank {
 // ======================================================================================
 template <int NE, int R, int NT, int L>
 __global__ void __launch_bounds__(NT, 1)
-k_backward_tangent(const Consts<NE> M, const Tape tp, int K, int Kp, const double* __restrict__ dr,
-                   const double* __restrict__ dw, const double* __restrict__ dvalT,
+k_backward_tangent(const Consts<NE> M, const Tape tp, int K, int Kp, const int* __restrict__ thi,
+                   const double* __restrict__ dr, const double* __restrict__ dw, const double* __restrict__ dvalT,
                    double* __restrict__ dpol, double* __restrict__ dvalue_first) {
   constexpr int LDA = NT * R;
   constexpr size_t GP = (size_t)NE * LDA;
@@ -56,9 +56,10 @@ k_backward_tangent(const Consts<NE> M, const Tape tp, int K, int Kp, const doubl
       ix[j] = rowok[j] ? __ldg(idxt + j * NT) : 0;
     }
   };
-  load_col(P - 1, 0, cf, ci);
+  const int Pe = thi ? min(P, thi[lane0 / kThiGroup]) : P;   // seeds are zero from period Pe on
+  if (Pe > 0) load_col(Pe - 1, 0, cf, ci);
   int pb = 0;
-  for (int t = P - 1; t >= 0; --t) {
+  for (int t = Pe - 1; t >= 0; --t) {
     const double rho = __ldg(tp.rho + t);
     double drl[L], dwl[L];
 #pragma unroll
@@ -210,8 +211,9 @@ __device__ __forceinline__ void gather_row(const double* __restrict__ xb, const 
 // ======================================================================================
 template <int NE, int R, int NT, int L>
 __global__ void __launch_bounds__(NT, 1)
-k_forward_tangent(const Consts<NE> M, const Tape tp, int K, int Kp, const double* __restrict__ dpol,
-                  const double* __restrict__ dD0, double* __restrict__ dkdpart, double* __restrict__ dD_last) {
+k_forward_tangent(const Consts<NE> M, const Tape tp, int K, int Kp, const int* __restrict__ thi,
+                  const double* __restrict__ dpol, const double* __restrict__ dD0, double* __restrict__ dkdpart,
+                  double* __restrict__ dD_last) {
   constexpr int LDA = NT * R, U = 2;
   constexpr size_t GP = (size_t)NE * LDA;
   extern __shared__ double smem[];
@@ -237,6 +239,7 @@ k_forward_tangent(const Consts<NE> M, const Tape tp, int K, int Kp, const double
       for (int e = 0; e < NE; ++e)
         Dd[l][j][e] = (dD0 && rowok[j] && laneon[l]) ? dD0[(size_t)(lane0 + l) * GP + e * LDA + j * NT + tid] : 0.0;
 
+  const int pe = thi ? min(P, thi[lane0 / kThiGroup]) : P;   // ṗ is zero (and unwritten) from period pe on
   // column in flight: ω, D/Δg, D_t, p_t, the row's source-range starts, and ṗ of the L lanes
   double cf[R][FW_NF], pdv[L][R]; int sv[R][3];
   auto load_col = [&](int t, int e, double (&c)[R][FW_NF], double (&pd)[L][R], int (&s)[R][3]) {
@@ -250,7 +253,7 @@ k_forward_tangent(const Consts<NE> M, const Tape tp, int K, int Kp, const double
 #pragma unroll
       for (int q = 0; q < 3; ++q) s[j][q] = rowok[j] ? __ldg(st + j * NT + q) : 0;
 #pragma unroll
-      for (int l = 0; l < L; ++l) pd[l][j] = (rowok[j] && laneon[l]) ? __ldcs(dpc + (size_t)l * LDA + j * NT) : 0.0;
+      for (int l = 0; l < L; ++l) pd[l][j] = (rowok[j] && laneon[l] && t < pe) ? __ldcs(dpc + (size_t)l * LDA + j * NT) : 0.0;
     }
   };
   load_col(0, 0, cf, pdv, sv);

@@ -63,8 +63,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // ======================================================================================
 template <int NE, int R, int NT, int L>
 __global__ void __launch_bounds__(NT, 1)
-k_backward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int Kp, int S, const double* __restrict__ dr,
-                       const double* __restrict__ dw, const double* __restrict__ dvalT,
+k_backward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int Kp, int S, const int* __restrict__ thi,
+                       const double* __restrict__ dr, const double* __restrict__ dw, const double* __restrict__ dvalT,
                        double* __restrict__ dpol, double* __restrict__ dvalue_first) {
   constexpr int LDA = NT * R, NW = NT / 32;
   constexpr size_t GP = (size_t)NE * LDA;
@@ -80,7 +80,9 @@ k_backward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int Kp, int S, 
   double* dws = drs + (size_t)L * P;
   double* rhos = dws + (size_t)L * P;
   uint64_t* full = reinterpret_cast<uint64_t*>(rhos + ((P + 1) & ~1));
-  const int nchunks = P * NE;
+  // seeds of this CTA's lanes are zero from period Pe on: V̇ and ṗ are exactly zero there, start at Pe-1
+  const int Pe = thi ? min(P, thi[lane0 / kThiGroup]) : P;
+  const int nchunks = Pe * NE;
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
@@ -95,15 +97,15 @@ k_backward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int Kp, int S, 
   }
   for (int t = tid; t < P; t += NT) rhos[t] = tp.rho[t];
   __syncthreads();
-  // chunk c lives at tape.bw + ((P-1-c/NE)*NE + c%NE)*CH
+  // chunk c lives at tape.bw + ((Pe-1-c/NE)*NE + c%NE)*CH
   if (tid == 0)
     for (int c = 0; c < S - 1 && c < nchunks; ++c) {
       mbar_expect_tx(&full[c], CH);
-      bulk_g2s(ring + (size_t)c * SLOT_D, tp.bw + ((size_t)(P - 1 - c / NE) * NE + c % NE) * CH, CH, &full[c]);
+      bulk_g2s(ring + (size_t)c * SLOT_D, tp.bw + ((size_t)(Pe - 1 - c / NE) * NE + c % NE) * CH, CH, &full[c]);
     }
-  // issue cursor: next chunk to request, its source and its slot
+  // issue cursor: next chunk to request, its source and its slot (only dereferenced while ci < nchunks)
   int ci = S - 1, ei = (S - 1) % NE, si = S - 1;
-  const unsigned char* isrc = tp.bw + ((size_t)(P - 1 - (S - 1) / NE) * NE + ei) * CH;
+  const unsigned char* isrc = tp.bw + ((ptrdiff_t)(Pe - 1 - (S - 1) / NE) * NE + ei) * CH;
 
   double Vd[L][R][NE];
 #pragma unroll
@@ -116,10 +118,10 @@ k_backward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int Kp, int S, 
             ? dvalT[(size_t)(lane0 + l) * GP + e * LDA + j * NT + tid] : 0.0;
 
   const size_t strideKL = (size_t)Kp * LDA;                        // doubles between columns of dpol
-  double* dp_t = dpol + ((size_t)(P - 1) * NE * Kp + lane0) * LDA + tid;
+  double* dp_t = dpol + ((ptrdiff_t)(Pe - 1) * NE * Kp + lane0) * LDA + tid;
   const double* sl = ring + tid;                                   // current slot, this thread's row
   int slot = 0, par = 0, pb = 0, iw = 0;
-  for (int t = P - 1; t >= 0; --t) {
+  for (int t = Pe - 1; t >= 0; --t) {
     const double rho = rhos[t];
     double drl[L], dwl[L];
 #pragma unroll
@@ -206,7 +208,8 @@ k_backward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int Kp, int S, 
 // ======================================================================================
 template <int NE, int R, int NT, int L>
 __global__ void __launch_bounds__(NT, 1)
-k_forward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int Kp, int S, const double* __restrict__ dpol,
+k_forward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int Kp, int S, const int* __restrict__ thi,
+                      const double* __restrict__ zeros, const double* __restrict__ dpol,
                       const double* __restrict__ dD0, double* __restrict__ dkdpart,
                       double* __restrict__ dD_last) {
   constexpr int LDA = NT * R, U = HANK_GATHER_U, NW = NT / 32;
@@ -234,11 +237,13 @@ k_forward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int Kp, int S, c
   // chunk c = t*NE + e: the tape chunk at tp.fw + c*CH and ṗ at dpol + (c*Kp + lane0)*LDA
   const size_t strideKL = (size_t)Kp * LDA;
   const double* psrc0 = dpol + (size_t)lane0 * LDA;
+  // beyond the seed horizon of this CTA's lanes ṗ is zero and was never written: stage the zero page
+  const int ce = thi ? min(P, thi[lane0 / kThiGroup]) * NE : nchunks;
   auto issue = [&](int c, int s) {
     double* dst = ring + (size_t)s * SLOT_D;
     mbar_expect_tx(&full[s], (uint32_t)CH + PDB);
     bulk_g2s(dst, tp.fw + (size_t)c * CH, CH, &full[s]);
-    bulk_g2s(dst + PD_OFF, psrc0 + (size_t)c * strideKL, PDB, &full[s]);
+    bulk_g2s(dst + PD_OFF, c < ce ? psrc0 + (size_t)c * strideKL : zeros, PDB, &full[s]);
   };
   if (tid == 0)
     for (int c = 0; c < S && c < nchunks; ++c) issue(c, c);

@@ -135,6 +135,29 @@ def test_side_stream_overlap_does_not_change_results(monkeypatch):
     assert np.array_equal(F, F2) and np.array_equal(JV, JV2)
 
 
+def test_jacobian_seed_horizons_do_not_change_columns(monkeypatch):
+    """hank_ks_jacobian_columns starts each group of unit-seed lanes at its seed period and stages zeros
+    beyond it (policy tangents there are exactly zero); HANK_NO_SKIP=1 sweeps every period instead."""
+    blk, x0, Z, P = _ks_block("ss_500x7_T300.npz")
+    n = 4 * P
+    blk.linearize(x0, Z)
+    J = blk.jacobian_columns(1, n + 1)
+    Jsub = blk.jacobian_columns(403, 431)
+    blk.close()
+    monkeypatch.setenv("HANK_NO_SKIP", "1")
+    blk2, _, _, _ = _ks_block("ss_500x7_T300.npz")
+    blk2.linearize(x0, Z)
+    J2 = blk2.jacobian_columns(1, n + 1)
+    cols = [3, 4, 7, n // 2 + 3, n - 1, n]
+    E = np.zeros((len(cols), n)); E[np.arange(len(cols)), np.array(cols) - 1] = 1.0
+    JE = blk2.jvp(E)
+    blk2.close()
+    assert np.all(np.isfinite(J))
+    assert close(J, J2), maxerr(J, J2)
+    assert close(Jsub, J2[:, 402:430]), maxerr(Jsub, J2[:, 402:430])
+    assert close(J[:, np.array(cols) - 1].T, JE)
+
+
 def test_fjvp_multi_wave_matches_jvp():
     """hank_ks_fjvp cuts a multi-wave pass at CTA-wave boundaries and downloads finished waves on the copy
     stream; every column must equal the one-pass hank_ks_jvp result."""
