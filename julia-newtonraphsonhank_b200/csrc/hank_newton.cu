@@ -15,6 +15,7 @@
 //             tangent lanes (hank_ks_jacobian_columns_dev, all SMs busy) so that the ~40 inner
 //             products J(x)·y become GEMVs instead of 40 strictly sequential single-lane sweeps.
 //             Same quantity (JVP(fullFunction, x, y) = J(x)·y), different summation order.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <limits>
@@ -57,7 +58,10 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 }
 
 // part[s][i] = Σ_{j in split s} A[i + j n] v[j]   (A column-major)
-__global__ void k_gemv_partial(const double* __restrict__ A, const double* __restrict__ v, int n, double* part) {
+// `done` (nullable): device flag of the speculative inner loop — once set, queued iterations are no-ops.
+__global__ void k_gemv_partial(const double* __restrict__ A, const double* __restrict__ v, int n, double* part,
+                               const double* done = nullptr) {
+  if (done && *done != 0.0) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int s = blockIdx.y;
   const int cs = (n + kSplit - 1) / kSplit;
@@ -68,7 +72,9 @@ __global__ void k_gemv_partial(const double* __restrict__ A, const double* __res
   part[(size_t)s * n + i] = acc;
 }
 // out = a − Σ_s part[s]   (rhs = F(x) − J(x)·y from the split GEMV)
-__global__ void k_sub_partial(const double* a, const double* __restrict__ part, int n, double* out) {
+__global__ void k_sub_partial(const double* a, const double* __restrict__ part, int n, double* out,
+                              const double* done = nullptr) {
+  if (done && *done != 0.0) return;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     double s = 0.0;
@@ -98,9 +104,12 @@ __global__ void k_norms(const double* a, const double* b, int n, double* scal) {
   if (threadIdx.x == 0) { scal[0] = sqrt(d); scal[1] = sqrt(s); }
 }
 // LU mode: R = Σ_s part; y_old = y; y = y_old + α R; norms (single block)
+// With eps_inner >= 0 (speculative loop): scal[3] counts the iterations that ran, scal[2] is raised as soon as
+// the reference's loop test `eps_inner < ||y - yold||` fails (also for a non-finite step).
 __global__ void k_update_from_partial(const double* __restrict__ part, int n, double alpha, double* R, double* y,
-                                      double* yold, double* scal) {
+                                      double* yold, double* scal, double eps_inner = -1.0) {
   __shared__ double red[33];
+  if (eps_inner >= 0.0 && scal[2] != 0.0) return;
   double d = 0.0, s = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     double r = 0.0;
@@ -113,7 +122,10 @@ __global__ void k_update_from_partial(const double* __restrict__ part, int n, do
   }
   d = block_sum(d, red);
   s = block_sum(s, red);
-  if (threadIdx.x == 0) { scal[0] = sqrt(d); scal[1] = sqrt(s); }
+  if (threadIdx.x == 0) {
+    scal[0] = sqrt(d); scal[1] = sqrt(s);
+    if (eps_inner >= 0.0) { scal[3] += 1.0; if (!(eps_inner < sqrt(d))) scal[2] = 1.0; }
+  }
 }
 __global__ void k_update_y(const double* __restrict__ R, int n, double alpha, double* y, double* yold, double* scal) {
   __shared__ double red[33];
@@ -228,9 +240,9 @@ struct NewtonBufs {
   double *x, *y, *yold, *Fx, *Lxy, *rhs, *R, *part, *scal, *Vb, *H, *gs, *nullvec, *J;
 };
 
-static int gemv_partial(hank_ctx* c, const double* A, const double* v, int n, double* part) {
+static int gemv_partial(hank_ctx* c, const double* A, const double* v, int n, double* part, const double* done = nullptr) {
   dim3 grid((n + 127) / 128, kSplit);
-  k_gemv_partial<<<grid, 128, 0, c->stream>>>(A, v, n, part);
+  k_gemv_partial<<<grid, 128, 0, c->stream>>>(A, v, n, part, done);
   c->launches++;
   return cuda_check(c, cudaGetLastError(), "k_gemv_partial");
 }
@@ -294,6 +306,7 @@ extern "C" int hank_newton_solve(hank_ctx* c, const double* Jbar, const double* 
                                  double eps_inner, int solver, double* x_out, double* stats, int* inner_counts) {
   if (!c || !Jbar || !x0 || !Z || !x_out) return HANK_ERR_ARG;
   CK(cudaSetDevice(c->device));
+  const auto t_entry = std::chrono::steady_clock::now();
   if (!c->ks_ready) return set_error(c, HANK_ERR_STATE, "hank_ks_configure has not been called");
   if (solver < 0 || solver > 2) return set_error(c, HANK_ERR_ARG, "solver must be 0 (gmres), 1 (lu) or 2 (lu, batched J(x))");
   const bool batched = solver == 2;
@@ -375,15 +388,26 @@ extern "C" int hank_newton_solve(hank_ctx* c, const double* Jbar, const double* 
   };
   const int nb = (n + 255) / 256;
   int outer = 1; long jvps = 0, fevals = 0, gm = 0;
+  // HANK_NEWTON_TRACE=1: host wall-clock split of the solve (setup incl. LU / linearisations / inner loops) on stderr
+  const bool trace = getenv("HANK_NEWTON_TRACE") != nullptr;
+  auto now = [&]() { if (trace) cudaStreamSynchronize(c->stream); return std::chrono::steady_clock::now(); };
+  auto ms_since = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::milli>(b - a).count();
+  };
+  double t_lin = 0.0, t_inner = 0.0;
+  const auto t_setup_end = now();
   // ||y|| for the first outer test (y = x0)
   k_norms<<<1, 1024, 0, c->stream>>>(B.y, B.y, n, B.scal);
   c->launches++;
   RC(read_scal());
   double ynorm = h_scal[1];
   while (eps < ynorm && outer < 100) {
+    const auto ta = now();
     RC(hank_ks_linearize_dev(c, B.x, c->d_Z, B.Fx));
     ++fevals;
     if (batched) RC(hank_ks_jacobian_columns_dev(c, 1, n + 1, Jx));
+    const auto tb = now();
+    t_lin += ms_since(ta, tb);
     k_fill<<<nb, 256, 0, c->stream>>>(B.yold, n, 1.0);
     k_fill<<<nb, 256, 0, c->stream>>>(B.R, n, 1.0);
     k_norms<<<1, 1024, 0, c->stream>>>(B.y, B.yold, n, B.scal);
@@ -391,6 +415,30 @@ extern "C" int hank_newton_solve(hank_ctx* c, const double* Jbar, const double* 
     RC(read_scal());
     double diff = h_scal[0];
     int inner = 0;
+    if (batched && eps_inner >= 0.0 && eps_inner < diff) {
+      // Speculative inner loop: iterations are queued kSpec at a time, the update kernel raises a device flag when
+      // the loop test fails and everything queued behind it returns at once, so the host synchronises once per
+      // kSpec iterations instead of once per iteration.  Same iterates, same count.
+      constexpr int kSpec = 4;
+      CK(cudaMemsetAsync(B.scal + 2, 0, 2 * sizeof(double), c->stream));
+      while (true) {
+        for (int q = 0; q < kSpec; ++q) {
+          RC(gemv_partial(c, Jx, B.y, n, B.part, B.scal + 2));
+          k_sub_partial<<<nb, 256, 0, c->stream>>>(B.Fx, B.part, n, B.rhs, B.scal + 2);
+          RC(gemv_partial(c, B.J, B.rhs, n, B.part, B.scal + 2));
+          k_update_from_partial<<<1, 1024, 0, c->stream>>>(B.part, n, 0.5, B.R, B.y, B.yold, B.scal, eps_inner);
+          c->launches += 2;
+        }
+        CK(cudaMemcpyAsync(h_scal, B.scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(c->h_status, c->d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (c->h_status[0] != 0) RC(hank_sync(c));
+        diff = h_scal[0]; ynorm = h_scal[1];
+        jvps += (long)h_scal[3] - inner; inner = (int)h_scal[3];
+        if (!std::isfinite(diff)) return set_error(c, HANK_ERR_NOCONV, "Newton inner iteration diverged (non-finite step)");
+        if (h_scal[2] != 0.0) break;
+      }
+    }
     while (eps_inner < diff) {
       if (batched) {
         RC(gemv_partial(c, Jx, B.y, n, B.part));
@@ -415,6 +463,7 @@ extern "C" int hank_newton_solve(hank_ctx* c, const double* Jbar, const double* 
       diff = h_scal[0]; ynorm = h_scal[1];
       if (!std::isfinite(diff)) return set_error(c, HANK_ERR_NOCONV, "Newton inner iteration diverged (non-finite step)");
     }
+    if (trace) t_inner += ms_since(tb, now());
     if (inner_counts && outer - 1 < 100) inner_counts[outer - 1] = inner;
     k_xmy<<<nb, 256, 0, c->stream>>>(B.x, B.y, n);
     c->launches++;
@@ -422,6 +471,9 @@ extern "C" int hank_newton_solve(hank_ctx* c, const double* Jbar, const double* 
   }
   CK(cudaMemcpyAsync(x_out, B.x, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  if (trace)
+    fprintf(stderr, "[hank_newton_solve] setup+LU %.2f ms, linearise%s %.2f ms, inner loops %.2f ms (%ld iterations)\n",
+            ms_since(t_entry, t_setup_end), batched ? "+J(x)" : "", t_lin, t_inner, jvps);
   if (stats) { stats[0] = outer - 1; stats[1] = (double)jvps; stats[2] = (double)fevals; stats[3] = ynorm; stats[4] = (double)gm; }
   if (eps < ynorm) return set_error(c, HANK_ERR_NOCONV, "Newton outer iteration cap (100) reached");
   return HANK_OK;
