@@ -1,7 +1,7 @@
 """Builds libhankb200.so (CUDA, sm_100a only) in-tree: csrc/*.cu -> lib/libhankb200.so.
 
 nvcc cross-compiles without a GPU.  Objects are compiled in parallel (one translation unit per
-n_e instantiation) and only when their sources changed.
+n_e instantiation and launcher group) and only when their sources changed.
 """
 import concurrent.futures as cf
 import glob
@@ -49,7 +49,7 @@ def build(force=False, verbose=False):
         if force or _newer(o, [s] + headers):
             jobs.append((s, o, o[:-2] + ".log"))
     if jobs:
-        with cf.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+        with cf.ThreadPoolExecutor(max_workers=min(os.cpu_count() or 8, len(jobs))) as ex:
             for f in [ex.submit(_compile, *j) for j in jobs]:
                 f.result()
                 if verbose:

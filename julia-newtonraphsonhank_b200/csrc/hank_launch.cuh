@@ -198,7 +198,9 @@ static int bt_launch(hank_ctx* c, int P, int K, const double* dr, const double* 
     if (S > 8) S = 8;
     if (S >= 2) {
       const size_t smem_t = fixed + (size_t)S * slot;
-      HANK_LAUNCH(KIND_BT, (k_backward_tangent_tma<NE, R, NT, L>), grid, NT, smem_t, M, c->tape, K, Kp, S, c->pass_thi, dr, dw, dvalT, dpol, dvf);
+      if (c->pass_thi)
+        HANK_LAUNCH(KIND_BT, (k_backward_tangent_tma<NE, R, NT, L, true>), grid, NT, smem_t, M, c->tape, K, Kp, S, c->pass_thi, dr, dw, dvalT, dpol, dvf);
+      HANK_LAUNCH(KIND_BT, (k_backward_tangent_tma<NE, R, NT, L, false>), grid, NT, smem_t, M, c->tape, K, Kp, S, (const int*)nullptr, dr, dw, dvalT, dpol, dvf);
     }
   }
   const size_t smem = (size_t)2 * L * LDA * sizeof(double);
@@ -217,7 +219,9 @@ static int ft_launch(hank_ctx* c, int P, int K, const double* dpol, double* dkdp
     if (S > 8) S = 8;
     if (S >= 2) {
       const size_t smem_t = fixed + (size_t)S * slot;
-      HANK_LAUNCH(KIND_FT, (k_forward_tangent_tma<NE, R, NT, L>), grid, NT, smem_t, M, c->tape, K, Kp, S, c->pass_thi, (const double*)c->d_zero, dpol, nullptr, dkdpart, nullptr);
+      if (c->pass_thi)
+        HANK_LAUNCH(KIND_FT, (k_forward_tangent_tma<NE, R, NT, L, true>), grid, NT, smem_t, M, c->tape, K, Kp, S, c->pass_thi, (const double*)c->d_zero, dpol, nullptr, dkdpart, nullptr);
+      HANK_LAUNCH(KIND_FT, (k_forward_tangent_tma<NE, R, NT, L, false>), grid, NT, smem_t, M, c->tape, K, Kp, S, (const int*)nullptr, (const double*)nullptr, dpol, nullptr, dkdpart, nullptr);
     }
   }
   const size_t smem = (size_t)4 * L * LDA * sizeof(double);

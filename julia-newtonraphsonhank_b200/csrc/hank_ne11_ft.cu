@@ -1,0 +1,5 @@
+// Instantiates the forward tangent launcher for n_e = 11 (see hank_launch.cuh).
+#include "hank_launch.cuh"
+namespace hank {
+template int Sweeps<11>::forward_tangent(hank_ctx*, int, int, const double*, double*, int*);
+}

@@ -1,0 +1,8 @@
+// Instantiates the primal sweep launchers for n_e = 11 (see hank_launch.cuh); one translation unit per
+// launcher group so that the build parallelises.
+#include "hank_launch.cuh"
+namespace hank {
+template int Sweeps<11>::backward_primal(hank_ctx*, int, const double*, const double*, const double*);
+template int Sweeps<11>::forward_primal(hank_ctx*, int, const double*, const double*, double*);
+template int Sweeps<11>::lanes_per_cta(hank_ctx*, int);
+}

@@ -61,7 +61,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // chunk c+S-1 is issued there (prefetch distance S-1 columns).
 // dpol: [P][NE][Kp][LDA], Kp a multiple of L (lanes >= K carry zero seeds).
 // ======================================================================================
-template <int NE, int R, int NT, int L>
+template <int NE, int R, int NT, int L, bool SKIP>
 __global__ void __launch_bounds__(NT, 1)
 k_backward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int Kp, int S, const int* __restrict__ thi,
                        const double* __restrict__ dr, const double* __restrict__ dw, const double* __restrict__ dvalT,
@@ -71,18 +71,19 @@ k_backward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int Kp, int S, 
   constexpr int CH = (int)bw_chunk_bytes<LDA>();
   constexpr int SLOT_D = CH / 8;
   extern __shared__ __align__(128) unsigned char smem_tma[];
-  const int n_a = M.n_a, P = M.P;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int lane0 = blockIdx.x * L;
+  // SKIP: seeds of this CTA's lanes are zero from period thi[group] on, so V̇ and ṗ are exactly zero there: the
+  // sweep of this CTA is the P-period sweep of a shorter horizon (only the seed rows keep the full stride).
+  // A template parameter, not a run-time test: the generic kernel keeps the code it was tuned with.
+  const int n_a = M.n_a, Pfull = M.P, P = SKIP ? min(M.P, thi[lane0 / kThiGroup]) : M.P;
   double* ring = reinterpret_cast<double*>(smem_tma);
   double* kbuf = ring + (size_t)S * SLOT_D;
   double* drs = kbuf + 2 * L * LDA;
   double* dws = drs + (size_t)L * P;
   double* rhos = dws + (size_t)L * P;
   uint64_t* full = reinterpret_cast<uint64_t*>(rhos + ((P + 1) & ~1));
-  // seeds of this CTA's lanes are zero from period Pe on: V̇ and ṗ are exactly zero there, start at Pe-1
-  const int Pe = thi ? min(P, thi[lane0 / kThiGroup]) : P;
-  const int nchunks = Pe * NE;
+  const int nchunks = P * NE;
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
@@ -92,20 +93,20 @@ k_backward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int Kp, int S, 
   for (int i = tid; i < L * P; i += NT) {
     const int l = i / P, t = i - l * P;
     const bool on = lane0 + l < K;
-    drs[i] = on ? dr[(size_t)(lane0 + l) * P + t] : 0.0;
-    dws[i] = on ? dw[(size_t)(lane0 + l) * P + t] : 0.0;
+    drs[i] = on ? dr[(size_t)(lane0 + l) * Pfull + t] : 0.0;
+    dws[i] = on ? dw[(size_t)(lane0 + l) * Pfull + t] : 0.0;
   }
   for (int t = tid; t < P; t += NT) rhos[t] = tp.rho[t];
   __syncthreads();
-  // chunk c lives at tape.bw + ((Pe-1-c/NE)*NE + c%NE)*CH
+  // chunk c lives at tape.bw + ((P-1-c/NE)*NE + c%NE)*CH
   if (tid == 0)
     for (int c = 0; c < S - 1 && c < nchunks; ++c) {
       mbar_expect_tx(&full[c], CH);
-      bulk_g2s(ring + (size_t)c * SLOT_D, tp.bw + ((size_t)(Pe - 1 - c / NE) * NE + c % NE) * CH, CH, &full[c]);
+      bulk_g2s(ring + (size_t)c * SLOT_D, tp.bw + ((size_t)(P - 1 - c / NE) * NE + c % NE) * CH, CH, &full[c]);
     }
   // issue cursor: next chunk to request, its source and its slot (only dereferenced while ci < nchunks)
   int ci = S - 1, ei = (S - 1) % NE, si = S - 1;
-  const unsigned char* isrc = tp.bw + ((ptrdiff_t)(Pe - 1 - (S - 1) / NE) * NE + ei) * CH;
+  const unsigned char* isrc = tp.bw + ((ptrdiff_t)(P - 1 - (S - 1) / NE) * NE + ei) * CH;
 
   double Vd[L][R][NE];
 #pragma unroll
@@ -118,10 +119,10 @@ k_backward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int Kp, int S, 
             ? dvalT[(size_t)(lane0 + l) * GP + e * LDA + j * NT + tid] : 0.0;
 
   const size_t strideKL = (size_t)Kp * LDA;                        // doubles between columns of dpol
-  double* dp_t = dpol + ((ptrdiff_t)(Pe - 1) * NE * Kp + lane0) * LDA + tid;
+  double* dp_t = dpol + ((ptrdiff_t)(P - 1) * NE * Kp + lane0) * LDA + tid;
   const double* sl = ring + tid;                                   // current slot, this thread's row
   int slot = 0, par = 0, pb = 0, iw = 0;
-  for (int t = Pe - 1; t >= 0; --t) {
+  for (int t = P - 1; t >= 0; --t) {
     const double rho = rhos[t];
     double drl[L], dwl[L];
 #pragma unroll
@@ -206,7 +207,7 @@ k_backward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int Kp, int S, 
 // A slot is only read before the column's barrier, so it is free right after it: chunk c+S is
 // issued after the barrier of column c (prefetch distance S columns).
 // ======================================================================================
-template <int NE, int R, int NT, int L>
+template <int NE, int R, int NT, int L, bool SKIP>
 __global__ void __launch_bounds__(NT, 1)
 k_forward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int Kp, int S, const int* __restrict__ thi,
                       const double* __restrict__ zeros, const double* __restrict__ dpol,
@@ -237,13 +238,14 @@ k_forward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int Kp, int S, c
   // chunk c = t*NE + e: the tape chunk at tp.fw + c*CH and ṗ at dpol + (c*Kp + lane0)*LDA
   const size_t strideKL = (size_t)Kp * LDA;
   const double* psrc0 = dpol + (size_t)lane0 * LDA;
-  // beyond the seed horizon of this CTA's lanes ṗ is zero and was never written: stage the zero page
-  const int ce = thi ? min(P, thi[lane0 / kThiGroup]) * NE : nchunks;
+  // SKIP: beyond the seed horizon of this CTA's lanes ṗ is zero and was never written — stage the zero page
+  const int ce = SKIP ? min(P, thi[lane0 / kThiGroup]) * NE : 0;
   auto issue = [&](int c, int s) {
     double* dst = ring + (size_t)s * SLOT_D;
     mbar_expect_tx(&full[s], (uint32_t)CH + PDB);
     bulk_g2s(dst, tp.fw + (size_t)c * CH, CH, &full[s]);
-    bulk_g2s(dst + PD_OFF, c < ce ? psrc0 + (size_t)c * strideKL : zeros, PDB, &full[s]);
+    if constexpr (SKIP) bulk_g2s(dst + PD_OFF, c < ce ? psrc0 + (size_t)c * strideKL : zeros, PDB, &full[s]);
+    else bulk_g2s(dst + PD_OFF, psrc0 + (size_t)c * strideKL, PDB, &full[s]);
   };
   if (tid == 0)
     for (int c = 0; c < S && c < nchunks; ++c) issue(c, c);
