@@ -158,6 +158,25 @@ def test_jacobian_seed_horizons_do_not_change_columns(monkeypatch):
     assert close(J[:, np.array(cols) - 1].T, JE)
 
 
+@pytest.mark.parametrize("fixture,switch", [("ss_500x7_T300.npz", "HANK_NO_TMA"), ("ss_1000x7_T300.npz", None),
+                                            ("ss_1000x7_T300.npz", "HANK_NO_TMA")])
+def test_jacobian_seed_horizons_other_kernels(fixture, switch, monkeypatch):
+    """Seed horizons in the register-prefetch kernels and in the two-rows-per-thread shapes: a column range
+    from the middle of the horizon equals generic JVPs of the same unit seeds (which sweep every period)."""
+    if switch:
+        monkeypatch.setenv(switch, "1")
+    blk, x0, Z, P = _ks_block(fixture)
+    n = 4 * P
+    blk.linearize(x0, Z)
+    lo, hi = 2 * P + 1, 2 * P + 41                      # 40 columns, 20 household lanes
+    Jc = blk.jacobian_columns(lo, hi)
+    E = np.zeros((hi - lo, n)); E[np.arange(hi - lo), np.arange(lo - 1, hi - 1)] = 1.0
+    JE = blk.jvp(E)
+    blk.close()
+    assert np.all(np.isfinite(Jc))
+    assert close(Jc.T, JE), maxerr(Jc.T, JE)
+
+
 def test_fjvp_multi_wave_matches_jvp():
     """hank_ks_fjvp cuts a multi-wave pass at CTA-wave boundaries and downloads finished waves on the copy
     stream; every column must equal the one-pass hank_ks_jvp result."""
