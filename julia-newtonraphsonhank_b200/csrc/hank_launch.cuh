@@ -74,8 +74,9 @@ static int launch_cluster(hank_ctx* c, int kind, KernelT kern, int block, size_t
 template <int NE, int R, int NT>
 static int bp_launch(hank_ctx* c, int P, const double* valueT, const double* r, const double* w) {
   const Consts<NE> M = make_consts<NE>(c, P);
-  if (!c->no_cluster && !c->no_dsmem && NE > 1 && bp_ds_smem<NE, NT * R>() <= (size_t)c->smem_max) {
-    // exchange through distributed shared memory (hank_primal_dsmem.cuh)
+  // exchange through distributed shared memory (hank_primal_dsmem.cuh); with two or more rows per thread the
+  // per-row remote stores cost more than the fence they replace (1000x7: 4.16 vs 3.97 us per period)
+  if constexpr (R == 1) if (!c->no_cluster && !c->no_dsmem && NE > 1 && bp_ds_smem<NE, NT * R>() <= (size_t)c->smem_max) {
     const size_t smem_d = bp_ds_smem<NE, NT * R>();
     int rc = c->gamma == 2.0
         ? launch_cluster<NE>(c, KIND_BP, k_backward_primal_ds<NE, R, NT, true>, NT, smem_d, "k_backward_primal_ds", M, c->tape,
