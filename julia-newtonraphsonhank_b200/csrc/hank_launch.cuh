@@ -199,7 +199,7 @@ static int bt_launch(hank_ctx* c, int P, int K, const double* dr, const double* 
     if (S > 8) S = 8;
     if (S >= 2) {
       const size_t smem_t = fixed + (size_t)S * slot;
-      if (c->pass_thi)
+      if constexpr (L != 6 && L != 3) if (c->pass_thi)   // (horizon passes never run the wide shapes backward)
         HANK_LAUNCH(KIND_BT, (k_backward_tangent_tma<NE, R, NT, L, true>), grid, NT, smem_t, M, c->tape, K, Kp, S, c->pass_thi, dr, dw, dvalT, dpol, dvf);
       HANK_LAUNCH(KIND_BT, (k_backward_tangent_tma<NE, R, NT, L, false>), grid, NT, smem_t, M, c->tape, K, Kp, S, (const int*)nullptr, dr, dw, dvalT, dpol, dvf);
     }
