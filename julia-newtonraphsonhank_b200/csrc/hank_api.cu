@@ -265,7 +265,8 @@ static int ensure_lanes(hank_ctx* c, int K) {
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   const size_t have = (size_t)c->Kcap * per_lane;
-  int Kmax = (int)std::min<size_t>((size_t)K, (size_t)(0.85 * (double)(free_b + have)) / per_lane - 16);
+  const long long fit = (long long)((0.85 * (double)(free_b + have)) / (double)per_lane) - 16;   // 16 lanes of stride padding
+  const int Kmax = (int)std::min<long long>((long long)K, std::max<long long>(fit, 0));
   if (Kmax < 1) return set_error(c, HANK_ERR_CUDA, "not enough device memory for one tangent lane");
   if (Kmax <= c->Kcap) return HANK_OK;
   dfree(c->d_dr); dfree(c->d_dw); dfree(c->d_dpol); dfree(c->d_dkdpart); dfree(c->d_dKD);
@@ -420,6 +421,7 @@ void hank_ctx_destroy(hank_ctx* c) {
   if (c->ev_bp) cudaEventDestroy(c->ev_bp);
   if (c->ev_fp) cudaEventDestroy(c->ev_fp);
   hank_comm_destroy(c);
+  newton_release(c);
   Tape& tp = c->tape;
   dfree(c->d_grid); dfree(c->d_valueT); dfree(c->d_D0); dfree(c->d_Pi); dfree(c->d_scatter); dfree(c->d_r); dfree(c->d_w);
   dfree(tp.pol); dfree(tp.bw); dfree(tp.rho); dfree(tp.fw); dfree(tp.mbr);
@@ -485,6 +487,7 @@ int hank_reserve_lanes(hank_ctx* c, int K) {
 
 int hank_set_terminal(hank_ctx* c, const double* v) {
   CK(cudaSetDevice(c->device));
+  RC(join_side(c));   // a side-stream forward sweep / residual of the last linearisation may still be in flight
   RC(copy_in(c, c->d_valueT, v, c->n_e));
   CK(cudaStreamSynchronize(c->stream));
   c->have_terminal = true; c->have_backward = false; c->linearized = false;
@@ -492,6 +495,7 @@ int hank_set_terminal(hank_ctx* c, const double* v) {
 }
 int hank_set_initial_dist(hank_ctx* c, const double* D0) {
   CK(cudaSetDevice(c->device));
+  RC(join_side(c));   // the side-stream forward primal sweep reads d_D0
   RC(copy_in(c, c->d_D0, D0, c->n_e));
   CK(cudaStreamSynchronize(c->stream));
   c->have_D0 = true; c->have_forward = false; c->linearized = false;
@@ -767,16 +771,20 @@ int hank_lottery(hank_ctx* c, const double* policy, int32_t* m, double* omega) {
   CK(cudaSetDevice(c->device));
   const int G = c->G;
   double* d_p = nullptr; int32_t* d_m = nullptr; double* d_o = nullptr;
-  RC(dalloc(c, &d_p, G)); RC(dalloc(c, &d_m, G)); RC(dalloc(c, &d_o, G));
-  CK(cudaMemcpyAsync(d_p, policy, G * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  k_lottery<<<nblk(G), 256, 0, c->stream>>>(c->d_grid, c->n_a, G, d_p, d_m, d_o);
-  c->launches++;
-  CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(m, d_m, G * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-  if (omega) CK(cudaMemcpyAsync(omega, d_o, G * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  cudaFree(d_p); cudaFree(d_m); cudaFree(d_o);
-  return HANK_OK;
+  auto run = [&]() -> int {
+    RC(dalloc(c, &d_p, G)); RC(dalloc(c, &d_m, G)); RC(dalloc(c, &d_o, G));
+    CK(cudaMemcpyAsync(d_p, policy, G * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    k_lottery<<<nblk(G), 256, 0, c->stream>>>(c->d_grid, c->n_a, G, d_p, d_m, d_o);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(m, d_m, G * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (omega) CK(cudaMemcpyAsync(omega, d_o, G * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return HANK_OK;
+  };
+  const int rc = run();
+  dfree(d_p); dfree(d_m); dfree(d_o);   // also on the error paths
+  return rc;
 }
 
 // ---- Krusell-Smith F and JVPs ---------------------------------------------------------------
@@ -790,6 +798,8 @@ int hank_ks_linearize_dev(hank_ctx* c, const double* x, const double* Z, double*
   if (!c->ks_ready) return set_error(c, HANK_ERR_STATE, "hank_ks_configure has not been called");
   if (!c->have_terminal || !c->have_D0) return set_error(c, HANK_ERR_STATE, "terminal value / initial distribution not set");
   const int P = c->P; const size_t n = (size_t)4 * P;
+  // the previous linearisation's forward sweep and residuals (side stream) read d_x, d_Z and d_KD
+  RC(join_side(c));
   if (x != c->d_x) CK(cudaMemcpyAsync(c->d_x, x, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   if (Z != c->d_Z) CK(cudaMemcpyAsync(c->d_Z, Z, P * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   k_extract_rw<<<nblk(P), 256, 0, c->stream>>>(c->d_x, P, c->d_r, c->d_w);
@@ -842,6 +852,7 @@ int hank_ks_jvp_dev(hank_ctx* c, int K, const double* V, double* JV) {
 int hank_ks_linearize(hank_ctx* c, const double* x, const double* Z, double* F) {
   CK(cudaSetDevice(c->device));
   const int P = c->P; const size_t n = (size_t)4 * P;
+  RC(join_side(c));   // before d_x / d_Z are overwritten
   CK(cudaMemcpyAsync(c->d_x, x, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_Z, Z, P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   RC(hank_ks_linearize_dev(c, c->d_x, c->d_Z, c->d_F));

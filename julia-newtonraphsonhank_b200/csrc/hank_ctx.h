@@ -48,6 +48,8 @@ struct hank_ctx {
   double *d_Jinv = nullptr, *d_newton = nullptr, *d_lu_work = nullptr;
   int* d_newton_i = nullptr;   // pivots + info
   size_t newton_bytes = 0, jinv_bytes = 0, lu_work_bytes = 0;
+  // cache of the preconditioner (J̅ or J̅⁻¹ in d_Jinv) across hank_newton_solve calls, keyed on a hash of J̅
+  bool jbar_valid = false, jbar_inverse = false; uint64_t jbar_key = 0; int jbar_n = 0;
 
   // NCCL
   void* nccl_comm = nullptr;
@@ -109,5 +111,6 @@ cudaEvent_t prof_begin(hank_ctx* c);
 void prof_end(hank_ctx* c, int kind, cudaEvent_t a);
 int set_error(hank_ctx* c, int code, const std::string& msg);
 int cuda_check(hank_ctx* c, cudaError_t e, const char* what);
+void newton_release(hank_ctx* c);   // destroys the cuSOLVER handle (hank_newton.cu)
 
 }  // namespace hank

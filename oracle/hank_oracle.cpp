@@ -482,6 +482,7 @@ int gmres(const double* A, int n, double* x, const double* b, int* iters_out) {
       if (!(iteration >= maxiter || current <= tol)) {  // done(g, iteration) with the old count
         beta = init();
         init_residual(beta);
+        current = beta;  // init_residual! also resets residual.current to the true residual of the new cycle
         std::fill(H.begin(), H.end(), 0.0);
       }
     }

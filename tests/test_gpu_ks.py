@@ -141,3 +141,38 @@ def test_egm_step_lanes(n_a, n_e, gamma, K):
     for x, y in zip(b, o):
         assert close(x, y), maxerr(x, y)
     blk.close()
+
+
+def test_newton_rejects_singular_jbar():
+    """A singular preconditioner must be reported by the LU (getrf info), not surface as a diverged iteration."""
+    from hankb200 import HankError
+    g = np.load(os.path.join(GOLD, "ks_100x3_T30.npz"))
+    m, T, blk = _block_from_golden(g)
+    blk.set_terminal(g["ss_value"]); blk.set_initial_dist(g["ss_D"])
+    blk.ks_configure(float(g["alpha"]), float(g["delta"]), float(g["ss_vars"][1]))
+    J = np.array(g["Jbar"]); J[:, 3] = 0.0; J[:, 7] = 0.0      # exactly singular: zero pivots in U
+    with pytest.raises(HankError) as ei:
+        blk.newton_solve(J, g["x0"], g["Z"], solver="lu")
+    assert "singular" in ei.value.msg, ei.value.msg
+    # the context (and the preconditioner cache) recover: same J̅ twice gives the same path, second call cached
+    x1, s1 = blk.newton_solve(g["Jbar"], g["x0"], g["Z"], solver="lu")
+    x2, s2 = blk.newton_solve(g["Jbar"], g["x0"], g["Z"], solver="lu")
+    assert np.array_equal(x1, x2) and s1["inner"] == s2["inner"] == list(g["newton_inner"])
+    blk.close()
+
+
+def test_relinearize_back_to_back_is_race_free():
+    """Two linearisations in a row with no tangent pass in between (zero-iteration Newton step, device-API users):
+    the second must not overwrite x / Z while the first one's side-stream forward sweep still reads them."""
+    g = np.load(os.path.join(GOLD, "ks_200x7_T40.npz"))
+    m, T, blk = _block_from_golden(g)
+    P = T - 1
+    blk.set_terminal(g["ss_value"]); blk.set_initial_dist(g["ss_D"])
+    blk.ks_configure(float(g["alpha"]), float(g["delta"]), float(g["ss_vars"][1]))
+    Fa = blk.linearize(g["x0"], g["Z"])
+    xb = g["x0"] * (1.0 + 1e-3 * np.cos(np.arange(4 * P)))
+    Fb = blk.linearize(xb, np.ones(P))
+    for _ in range(5):
+        assert np.array_equal(blk.linearize(g["x0"], g["Z"]), Fa)
+        assert np.array_equal(blk.linearize(xb, np.ones(P)), Fb)
+    blk.close()
