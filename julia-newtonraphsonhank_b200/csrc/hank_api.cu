@@ -373,6 +373,9 @@ int hank_ctx_create(hank_ctx** out, int device, int n_a, int n_e, int T, const d
   { const char* nt = getenv("HANK_NO_CLUSTER"); c->no_cluster = nt && nt[0] == '1'; }
   { const char* nt = getenv("HANK_NO_DSMEM"); c->no_dsmem = nt && nt[0] == '1'; }
   { const char* nt = getenv("HANK_NO_SKIP"); c->no_skip = nt && nt[0] == '1'; }
+  { const char* nt = getenv("HANK_NO_ROWSPLIT"); c->no_rowsplit = nt && nt[0] == '1'; }
+  { const char* nt = getenv("HANK_RS_MAXK"); c->rs_max_k = nt ? atoi(nt) : 0; }
+  { const char* nt = getenv("HANK_RS_NO_MULTI"); c->rs_no_multi = nt && nt[0] == '1'; }
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   {
     int lo = 0, hi = 0;
@@ -430,6 +433,7 @@ void hank_ctx_destroy(hank_ctx* c) {
   dfree(c->d_jac_idx); dfree(c->d_thi); dfree(c->d_zero); dfree(c->d_xch); dfree(c->d_kdpart); dfree(c->d_KD); dfree(c->d_dkdpart); dfree(c->d_dKD); dfree(c->d_status);
   dfree(c->d_x); dfree(c->d_Z); dfree(c->d_F); dfree(c->d_V); dfree(c->d_JV);
   dfree(c->d_Jinv); dfree(c->d_newton); dfree(c->d_newton_i); dfree(c->d_lu_work);
+  dfree(c->tape_rs_bw); dfree(c->tape_rs_fw);
   for (auto& r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   if (c->h_status) cudaFreeHost(c->h_status);
@@ -590,6 +594,7 @@ int hank_forward_policies(hank_ctx* c, const double* policy, int K, const double
   if (K > 0) { RC(ensure_lanes(c, K)); if (K > c->Kcap) return set_error(c, HANK_ERR_ARG, "K exceeds device memory"); }
   RC(copy_in(c, c->tape.pol, policy, (size_t)P * c->n_e));
   const size_t Kpf = K > 0 ? (size_t)lane_stride(c, K) : 0;
+  c->Kp_last = (int)Kpf; c->dpol_rs = false;
   for (int l = 0; l < K; ++l)  // caller [K][P][n_e][n_a] -> device [P][n_e][Kp][lda]
     CK(cudaMemcpy2DAsync(c->d_dpol + (size_t)l * c->lda, Kpf * c->lda * 8, dpolicy + (size_t)l * P * c->G,
                          (size_t)c->n_a * 8, (size_t)c->n_a * 8, (size_t)P * c->n_e, cudaMemcpyDefault, c->stream));
@@ -647,7 +652,7 @@ int hank_egm_step(hank_ctx* c, const double* value_next, const double* dvalue_ne
     RC(copy_out(c, dvalue, c->d_dvalue_first, (size_t)K * c->n_e));
     for (int l = 0; l < K; ++l)  // device [1][n_e][K][lda] -> caller [K][n_e][n_a]
       CK(cudaMemcpy2DAsync(dpolicy + (size_t)l * c->G, (size_t)c->n_a * 8, c->d_dpol + (size_t)l * c->lda,
-                           (size_t)lane_stride(c, K) * c->lda * 8, (size_t)c->n_a * 8, c->n_e, cudaMemcpyDefault, c->stream));
+                           (size_t)c->Kp_last * c->lda * 8, (size_t)c->n_a * 8, c->n_e, cudaMemcpyDefault, c->stream));
   }
   return check_status(c);
 }
@@ -721,7 +726,7 @@ int hank_vfi(hank_ctx* c, double r, double w, int K, const double* dr, const dou
     RC(copy_out(c, dvalue, (const double*)c->d_dvalue_first, (size_t)K * c->n_e));
     for (int l = 0; l < K; ++l)
       CK(cudaMemcpy2DAsync(dpolicy + (size_t)l * c->G, (size_t)c->n_a * 8, c->d_dpol + (size_t)l * c->lda,
-                           (size_t)lane_stride(c, K) * c->lda * 8, (size_t)c->n_a * 8, c->n_e, cudaMemcpyDefault, c->stream));
+                           (size_t)c->Kp_last * c->lda * 8, (size_t)c->n_a * 8, c->n_e, cudaMemcpyDefault, c->stream));
   }
   return check_status(c);
 }
@@ -733,7 +738,20 @@ int hank_get_policy(hank_ctx* c, int t, int lane, double* out) {
   if (lane == 0) RC(copy_out(c, out, (const double*)(c->tape.pol + (size_t)(t - 1) * c->Gp), c->n_e));
   else  // tangents are [t][e][K][lda]
   {
-    const size_t Kp = (size_t)lane_stride(c, c->K_last);
+    const size_t Kp = (size_t)c->Kp_last;
+    if (c->dpol_rs) {
+      // written by the row-split backward sweep: [t][cluster][rank][e][l][NT]
+      const int L = c->dpol_rs_L, NC = c->dpol_rs_NC, NT = c->lda / NC, cl = (lane - 1) / L, l = (lane - 1) % L;
+      const double* base = c->d_dpol + (((size_t)(t - 1) * c->dpol_rs_ncl + cl) * NC) * ((size_t)c->n_e * L * NT);
+      const size_t full = (size_t)c->n_a / NT, rem = (size_t)c->n_a % NT;
+      for (int e = 0; e < c->n_e; ++e) {
+        const double* src = base + ((size_t)e * L + l) * NT;
+        if (full) CK(cudaMemcpy2DAsync(out + (size_t)e * c->n_a, (size_t)NT * 8, src, (size_t)c->n_e * L * NT * 8, (size_t)NT * 8, full,
+                                       cudaMemcpyDefault, c->stream));
+        if (rem) CK(cudaMemcpyAsync(out + (size_t)e * c->n_a + full * NT, src + full * ((size_t)c->n_e * L * NT), rem * 8,
+                                    cudaMemcpyDefault, c->stream));
+      }
+    } else
     CK(cudaMemcpy2DAsync(out, (size_t)c->n_a * 8, c->d_dpol + ((size_t)(t - 1) * c->n_e * Kp + (lane - 1)) * c->lda,
                          Kp * c->lda * 8, (size_t)c->n_a * 8, c->n_e, cudaMemcpyDefault, c->stream));
   }

@@ -68,6 +68,15 @@ struct hank_ctx {
   bool no_wide = false;          // HANK_NO_WIDE=1: never use the 256-thread / 6-lane tangent shape
   bool no_tma = false;           // HANK_NO_TMA=1: use the register-prefetch tangent kernels
   bool no_skip = false;          // HANK_NO_SKIP=1: unit-seed Jacobian lanes sweep all periods
+  bool no_rowsplit = false;      // HANK_NO_ROWSPLIT=1: never split a lane group's rows over a cluster
+  bool rs_no_multi = false;      // HANK_RS_NO_MULTI=1: no multi-lane row-split clusters (mid lane counts run one CTA per lane)
+  int rs_max_k = 0;              // HANK_RS_MAXK: lane count up to which 1-lane row-split clusters are used (0: sm_count / NC)
+  int rs_cap[2] = {-1, -1};      // resident clusters of the 1-lane / 4-lane row-split shape (-1: not asked yet)
+  // row-block-major copies of the tape for the row-split kernels, and the layout of the policy tangents in d_dpol
+  unsigned char *tape_rs_bw = nullptr, *tape_rs_fw = nullptr;
+  bool tape_rs_bw_valid = false, tape_rs_fw_valid = false;
+  bool dpol_rs = false; int dpol_rs_L = 0, dpol_rs_NC = 0, dpol_rs_ncl = 0;   // d_dpol is [t][cluster][rank][e][l][NT]
+  int Kp_last = 0;               // lane stride of the policy tangents written by the last backward tangent sweep
   // Seed horizons of the pass in flight (hank_ks_jacobian_columns): lanes come in groups of kThiGroup
   // whose seeds are zero from period pass_thi[group] on, so the backward tangent starts there and the
   // forward tangent reads zeros instead of policy tangents beyond it.  Null for generic seeds.
@@ -104,6 +113,12 @@ struct Sweeps {
   static int forward_primal(hank_ctx* c, int P, const double* D0, const double* pol, double* KD);
   static int forward_tangent(hank_ctx* c, int P, int K, const double* dpol, double* dkdpart, int* nw_out);
   static int lanes_per_cta(hank_ctx* c, int K);
+  // rows of a lane group split over a cluster of NC CTAs (hank_tangent_rowsplit.cuh); -1: shape not available
+  static int backward_tangent_rs(hank_ctx* c, int NC, int NT, int L, int GC, int P, int K, const double* dr,
+                                 const double* dw, double* dpol);
+  static int forward_tangent_rs(hank_ctx* c, int NC, int NT, int L, int GC, int P, int K, const double* dpol,
+                                double* dkdpart);
+  static int rs_max_clusters(hank_ctx* c, int NC, int NT, int L, int GC);   // clusters of that shape resident at once
 };
 
 enum { KIND_BP = 0, KIND_BT = 1, KIND_FP = 2, KIND_FT = 3 };

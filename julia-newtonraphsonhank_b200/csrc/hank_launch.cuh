@@ -70,10 +70,36 @@ static int launch_cluster(hank_ctx* c, int kind, KernelT kern, int block, size_t
   return cuda_check(c, e, name);
 }
 
+// Launch `kern` on `grid` CTAs in clusters of `cluster` CTAs.  Returns -1 if such a cluster cannot be scheduled.
+template <typename KernelT, typename... Args>
+static int launch_cluster_grid(hank_ctx* c, int kind, KernelT kern, int grid, int cluster, int block, size_t smem,
+                               const char* name, Args... args) {
+  if (cluster > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  int rc = set_smem(c, kern, smem);
+  if (rc) return rc;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int ncl = 0;
+  if (cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg) != cudaSuccess || ncl < 1) { cudaGetLastError(); return -1; }
+  cudaEvent_t ev = prof_begin(c);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args...);
+  prof_end(c, kind, ev);
+  c->launches++;
+  return cuda_check(c, e, name);
+}
+
 // ---- backward primal -------------------------------------------------------------------
 template <int NE, int R, int NT>
 static int bp_launch(hank_ctx* c, int P, const double* valueT, const double* r, const double* w) {
   const Consts<NE> M = make_consts<NE>(c, P);
+  c->tape_rs_bw_valid = false;
   // exchange through distributed shared memory (hank_primal_dsmem.cuh); with two or more rows per thread the
   // per-row remote stores cost more than the fence they replace (1000x7: 4.16 vs 3.97 us per period)
   if constexpr (R == 1) if (!c->no_cluster && !c->no_dsmem && NE > 1 && bp_ds_smem<NE, NT * R>() <= (size_t)c->smem_max) {
@@ -114,6 +140,7 @@ int Sweeps<NE>::backward_primal(hank_ctx* c, int P, const double* valueT, const 
 template <int NE, int R, int NT, int CS>
 static int fp_launch(hank_ctx* c, int P, const double* D0, const double* pol, double* KD) {
   const Consts<NE> M = make_consts<NE>(c, P);
+  c->tape_rs_fw_valid = false;
   constexpr int LDA = NT * R;
   if (!c->no_cluster && !c->no_dsmem && NE > 1 && CS == NE && fp_ds_smem<NE, LDA>() <= (size_t)c->smem_max) {
     int rc = launch_cluster<NE>(c, KIND_FP, k_forward_primal_ds<NE, R, NT>, NT, fp_ds_smem<NE, LDA>(), "k_forward_primal_ds", M,
@@ -155,15 +182,44 @@ int Sweeps<NE>::forward_primal(hank_ctx* c, int P, const double* D0, const doubl
 // 512 threads x R rows hold L*R <= 4; 256 threads x 2R rows hold 6 lanes at LDA 512 (3 at 1024),
 // which cuts the tape bytes staged per lane by a third.  Deeper lanes are only used once every SM
 // has a CTA.
-struct TangentCfg { int NT, R, L; };
+struct TangentCfg { int NT, R, L; int NC = 0, GC = 0, LA = 0; };   // NC > 0: rows split over a cluster (hank_tangent_rowsplit.cuh)
 // waves(K, L) * relative cost of one wave with L lanes per CTA (measured at 500x7: a 6-lane wave
 // costs 1.6x a 4-lane wave, a 4-lane wave 1.9x a 1-lane wave; profiles/r01_notes.md)
 static double cfg_cost(int K, int L, int sm, double wave_cost) {
   const int ctas = (K + L - 1) / L;
   return (double)((ctas + sm - 1) / sm) * wave_cost;
 }
-static TangentCfg tangent_cfg(const hank_ctx* c, int K) {
+// Row-split cluster shapes for passes with few lanes: one lane per cluster of 8 CTAs while every lane can have a
+// cluster of its own, then wider row blocks (see below) while one wave of clusters still covers the pass.  How many clusters
+// can be resident at once (an 8-CTA cluster has to fit inside one GPC) is asked of the driver once per shape.
+template <int NE>
+static bool rowsplit_cfg(const hank_ctx* c, int K, TangentCfg* out) {
+  if (c->no_rowsplit || K < 1) return false;
+  const int ne = c->n_e;
+  const int nc = c->lda == 256 ? 4 : 8, nt = c->lda / nc;
+  // a whole period per exchange when the period's tape rows fit the ring twice over, else column by column
+  const bool whole = (size_t)2 * ne * (52 * nt) + (size_t)2 * ne * nt * 8 + 1024 <= (size_t)c->smem_max && c->lda <= 1024;
+  const TangentCfg one = whole ? TangentCfg{nt, 1, 1, nc, ne, 0} : TangentCfg{nt, 1, 1, nc, 1, 2};
+  hank_ctx* cm = const_cast<hank_ctx*>(c);
+  if (c->rs_cap[0] < 0) cm->rs_cap[0] = Sweeps<NE>::rs_max_clusters(cm, one.NC, one.NT, one.L, one.GC);
+  const int max_k = c->rs_max_k > 0 ? c->rs_max_k : c->rs_cap[0];
+  if (K <= max_k) { *out = one; return true; }
+  if (c->rs_no_multi) return false;
+  // more lanes than 8-CTA clusters fit: 500 rows -> one lane per CLUSTER OF 2 (a whole period per exchange);
+  // 1000 / 2000 rows -> 2 lanes per cluster of 4, column by column; while one wave of clusters covers the pass
+  TangentCfg mid; int lm;
+  if (c->lda == 512) { mid = TangentCfg{256, 1, 1, 2, ne, 0}; lm = 1; }
+  else if (c->lda >= 1024) { mid = TangentCfg{c->lda / 4, 1, 2, 4, 1, 2}; lm = 2; }
+  else return false;
+  if (c->rs_cap[1] < 0) cm->rs_cap[1] = Sweeps<NE>::rs_max_clusters(cm, mid.NC, mid.NT, mid.L, mid.GC);
+  if ((K + lm - 1) / lm <= c->rs_cap[1]) { *out = mid; return true; }
+  return false;
+}
+template <int NE>
+static TangentCfg tangent_cfg(const hank_ctx* c, int K, bool allow_rowsplit = true) {
   const int sm = c->sm_count;
+  TangentCfg rs;
+  if (allow_rowsplit && rowsplit_cfg<NE>(c, K, &rs)) return rs;
   switch (c->lda) {
     case 256: return {256, 1, K >= 4 * sm ? 4 : (K >= 2 * sm ? 2 : 1)};
     case 512: {
@@ -183,7 +239,7 @@ static TangentCfg tangent_cfg(const hank_ctx* c, int K) {
   }
 }
 template <int NE>
-int Sweeps<NE>::lanes_per_cta(hank_ctx* c, int K) { return tangent_cfg(c, K).L; }
+int Sweeps<NE>::lanes_per_cta(hank_ctx* c, int K) { return tangent_cfg<NE>(c, K).L; }
 
 template <int NE, int R, int NT, int L>
 static int bt_launch(hank_ctx* c, int P, int K, const double* dr, const double* dw, const double* dvalT,
@@ -191,6 +247,7 @@ static int bt_launch(hank_ctx* c, int P, int K, const double* dr, const double* 
   const Consts<NE> M = make_consts<NE>(c, P);
   const int grid = (K + L - 1) / L;
   const int Kp = c->pass_Kp ? c->pass_Kp : grid * L;   // lane stride of the policy tangents (>= grid * L)
+  c->Kp_last = Kp; c->dpol_rs = false;
   constexpr int LDA = NT * R;
   if constexpr (LDA <= 1024) if (!c->no_tma) {  // TMA-staged tape ring (hank_tangent_tma.cuh)
     const size_t slot = bw_chunk_bytes<LDA>();
@@ -258,7 +315,14 @@ int Sweeps<NE>::backward_tangent(hank_ctx* c, int P, int K, const double* dr, co
   // With seed horizons (descending over the lanes) a CTA's work shrinks with its index, so the block
   // scheduler packs the short CTAs behind the long ones: 4-lane CTAs finish in one full-length sweep where
   // the 6-lane shape would need one (slower) full-length wave as well.
-  TangentCfg cfg = tangent_cfg(c, K);
+  // single-step callers (hank_egm_step, hank_vfi) seed V̇ and read it back: one-CTA kernels only
+  const bool allow_rs = dvalT == nullptr && dvf == nullptr;
+  TangentCfg cfg = tangent_cfg<NE>(c, K, allow_rs);
+  if (cfg.NC > 0) {
+    const int rc = Sweeps<NE>::backward_tangent_rs(c, cfg.NC, cfg.NT, cfg.L, cfg.GC, P, K, dr, dw, dpol);
+    if (rc >= 0) return rc;
+    return set_error(c, 1, "row-split cluster launch of the backward tangent sweep failed (cluster not schedulable)");
+  }
   if (c->pass_thi && c->lda == 512 && cfg.L == 6) cfg = {512, 1, 4};
   if (c->pass_thi && c->lda == 1024 && cfg.L == 3) cfg = {512, 2, 2};
   TANGENT_DISPATCH(cfg, bt_launch, c, P, K, dr, dw, dvalT, dpol, dvf);
@@ -266,8 +330,15 @@ int Sweeps<NE>::backward_tangent(hank_ctx* c, int P, int K, const double* dr, co
 template <int NE>
 int Sweeps<NE>::forward_tangent(hank_ctx* c, int P, int K, const double* dpol, double* dkdpart, int* nw_out) {
   if (c->lda > 2048) return set_error(c, 1, "n_a > 2048 is not supported");
-  *nw_out = tangent_cfg(c, K).NT / 32;
-  TANGENT_DISPATCH(tangent_cfg(c, K), ft_launch, c, P, K, dpol, dkdpart);
+  const TangentCfg cfg = tangent_cfg<NE>(c, K);
+  if (cfg.NC > 0) {
+    *nw_out = cfg.NC;
+    const int rc = Sweeps<NE>::forward_tangent_rs(c, cfg.NC, cfg.NT, cfg.L, cfg.GC, P, K, dpol, dkdpart);
+    if (rc >= 0) return rc;
+    return set_error(c, 1, "row-split cluster launch of the forward tangent sweep failed (cluster not schedulable)");
+  }
+  *nw_out = cfg.NT / 32;
+  TANGENT_DISPATCH(cfg, ft_launch, c, P, K, dpol, dkdpart);
 }
 
 }  // namespace hank

@@ -1,0 +1,124 @@
+// hank_launch_rs.cuh — launchers of the row-split cluster tangent sweeps (hank_tangent_rowsplit.cuh), templated
+// on n_e.  Included only by hank_ne*_rs.cu so that these kernels compile in their own translation units.
+#pragma once
+#include "hank_launch.cuh"
+#include "hank_tangent_rowsplit.cuh"
+
+namespace hank {
+
+// ---- row-split cluster launchers ---------------------------------------------------------
+static int rs_ring_slots(const hank_ctx* c, size_t fixed, size_t slot, int min_slots, int max_slots) {
+  if (fixed + (size_t)min_slots * slot > (size_t)c->smem_max) return 0;
+  const int s = (int)(((size_t)c->smem_max - fixed) / slot);
+  return s > max_slots ? max_slots : s;
+}
+// Row-block-major copies of the tape (k_tape_rowblocks_*), made once per linearisation on first use.
+static int ensure_tape_rs(hank_ctx* c, int P, int NT, bool forward) {
+  const size_t ncols = (size_t)c->P_alloc * c->n_e;
+  const size_t bwb = ncols * 52 * (size_t)c->lda, fwb = ncols * (36 * (size_t)c->lda + 16 * (size_t)(c->lda / NT));
+  if (!c->tape_rs_bw) {
+    int rc = cuda_check(c, cudaMalloc((void**)&c->tape_rs_bw, bwb), "cudaMalloc(tape_rs_bw)");
+    if (rc) return rc;
+    rc = cuda_check(c, cudaMalloc((void**)&c->tape_rs_fw, fwb), "cudaMalloc(tape_rs_fw)");
+    if (rc) return rc;
+  }
+  const size_t n = (size_t)P * c->n_e * c->lda;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  if (!forward && !c->tape_rs_bw_valid) {
+    k_tape_rowblocks_bw<<<grid, 256, 0, c->stream>>>(c->tape.bw, c->tape_rs_bw, P * c->n_e, c->n_e, c->lda, NT);
+    c->launches++; c->tape_rs_bw_valid = true;
+  }
+  if (forward && !c->tape_rs_fw_valid) {
+    k_tape_rowblocks_fw<<<grid, 256, 0, c->stream>>>(c->tape.fw, c->tape_rs_fw, P * c->n_e, c->n_e, c->lda, NT);
+    c->launches++; c->tape_rs_fw_valid = true;
+  }
+  return cuda_check(c, cudaGetLastError(), "k_tape_rowblocks");
+}
+template <int NE, int NC, int NT, int L, int GC, int LA>
+static int bt_rs_launch(hank_ctx* c, int P, int K, const double* dr, const double* dw, double* dpol) {
+  const Consts<NE> M = make_consts<NE>(c, P);
+  const int ncl = (K + L - 1) / L;
+  c->Kp_last = ncl * L;
+  c->dpol_rs = true; c->dpol_rs_L = L; c->dpol_rs_NC = NC; c->dpol_rs_ncl = ncl;
+  const size_t slot = (size_t)GC * rs_bw_col_bytes<NT>();
+  const int S = rs_ring_slots(c, rs_bw_smem<NT, L, GC, LA>(0), slot + 16, LA + 2, GC == 1 ? 3 * NE : 6);
+  if (S < LA + 2) return -1;
+  int rc = ensure_tape_rs(c, P, NT, false);
+  if (rc) return rc;
+  return launch_cluster_grid(c, KIND_BT, k_backward_tangent_rs<NE, NC, NT, L, GC, LA>, ncl * NC, NC, NT + 32,
+                             rs_bw_smem<NT, L, GC, LA>(S), "k_backward_tangent_rs", M, c->tape, (const unsigned char*)c->tape_rs_bw, K, S,
+                             c->pass_thi, dr, dw, dpol);
+}
+template <int NE, int NC, int NT, int L, int GC, int LA>
+static int ft_rs_launch(hank_ctx* c, int P, int K, const double* dpol, double* dkdpart) {
+  const Consts<NE> M = make_consts<NE>(c, P);
+  const int ncl = (K + L - 1) / L;
+  // ṗ comes from this pass's row-split backward sweep (same shape), or from the caller in the column-major layout
+  const bool pd_rs = c->dpol_rs && c->dpol_rs_L == L && c->dpol_rs_NC == NC && c->dpol_rs_ncl == ncl;
+  const int Kp = c->pass_Kp ? c->pass_Kp : ncl * L;
+  const size_t slot = (size_t)GC * rs_fw_col_bytes<NT, L>();
+  const int S = rs_ring_slots(c, rs_fw_smem<NT, L, GC, LA>(0), slot + 16, LA + 2, GC == 1 ? 3 * NE : 6);
+  if (S < LA + 2) return -1;
+  int rc = ensure_tape_rs(c, P, NT, true);
+  if (rc) return rc;
+  return launch_cluster_grid(c, KIND_FT, k_forward_tangent_rs<NE, NC, NT, L, GC, LA>, ncl * NC, NC, NT + 32,
+                             rs_fw_smem<NT, L, GC, LA>(S), "k_forward_tangent_rs", M, (const unsigned char*)c->tape_rs_fw, K, Kp, S,
+                             c->pass_thi, (const double*)c->d_zero, dpol, pd_rs ? 1 : 0, dkdpart);
+}
+// clusters of this shape that can be resident at once (the smaller of the two sweeps' answers)
+template <int NE, int NC, int NT, int L, int GC, int LA>
+static int rs_cap_shape(hank_ctx* c) {
+  int cap = 1 << 30;
+  auto ask = [&](auto kern, size_t smem) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); cap = 0; return; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(NC * 64); cfg.blockDim = dim3(NT + 32); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = NC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    cap = n < cap ? n : cap;
+  };
+  const int Sb = rs_ring_slots(c, rs_bw_smem<NT, L, GC, LA>(0), (size_t)GC * rs_bw_col_bytes<NT>() + 16, LA + 2, GC == 1 ? 3 * NE : 6);
+  const int Sf = rs_ring_slots(c, rs_fw_smem<NT, L, GC, LA>(0), (size_t)GC * rs_fw_col_bytes<NT, L>() + 16, LA + 2, GC == 1 ? 3 * NE : 6);
+  if (Sb < LA + 2 || Sf < LA + 2) return 0;
+  ask(k_backward_tangent_rs<NE, NC, NT, L, GC, LA>, rs_bw_smem<NT, L, GC, LA>(Sb));
+  ask(k_forward_tangent_rs<NE, NC, NT, L, GC, LA>, rs_fw_smem<NT, L, GC, LA>(Sf));
+  return cap;
+}
+// shapes instantiated per n_e (rowsplit_cfg only returns these)
+#define ROWSPLIT_DISPATCH(g, FN, ...)                                                                   \
+  do {                                                                                                  \
+    if (g.NC == 4 && g.NT == 64 && g.L == 1 && g.GC == NE) return FN<NE, 4, 64, 1, NE, 0>(__VA_ARGS__);   \
+    if (g.NC == 8 && g.NT == 64 && g.L == 1 && g.GC == NE) return FN<NE, 8, 64, 1, NE, 0>(__VA_ARGS__);   \
+    if (g.NC == 8 && g.NT == 128 && g.L == 1 && g.GC == NE) return FN<NE, 8, 128, 1, NE, 0>(__VA_ARGS__); \
+    if (g.NC == 8 && g.NT == 256 && g.L == 1 && g.GC == 1) return FN<NE, 8, 256, 1, 1, 2>(__VA_ARGS__);   \
+    if (g.NC == 2 && g.NT == 256 && g.L == 1 && g.GC == NE) return FN<NE, 2, 256, 1, NE, 0>(__VA_ARGS__);  \
+    if (g.NC == 4 && g.NT == 256 && g.L == 2 && g.GC == 1) return FN<NE, 4, 256, 2, 1, 2>(__VA_ARGS__);   \
+    if (g.NC == 4 && g.NT == 512 && g.L == 2 && g.GC == 1) return FN<NE, 4, 512, 2, 1, 2>(__VA_ARGS__);   \
+  } while (0)
+template <int NE>
+int Sweeps<NE>::rs_max_clusters(hank_ctx* c, int NC, int NT, int L, int GC) {
+  const TangentCfg g{NT, 1, L, NC, GC, 0};
+  ROWSPLIT_DISPATCH(g, rs_cap_shape, c);
+  return 0;
+}
+template <int NE>
+int Sweeps<NE>::backward_tangent_rs(hank_ctx* c, int NC, int NT, int L, int GC, int P, int K, const double* dr,
+                                    const double* dw, double* dpol) {
+  const TangentCfg g{NT, 1, L, NC, GC, 0};
+  ROWSPLIT_DISPATCH(g, bt_rs_launch, c, P, K, dr, dw, dpol);
+  return -1;
+}
+template <int NE>
+int Sweeps<NE>::forward_tangent_rs(hank_ctx* c, int NC, int NT, int L, int GC, int P, int K, const double* dpol,
+                                   double* dkdpart) {
+  const TangentCfg g{NT, 1, L, NC, GC, 0};
+  ROWSPLIT_DISPATCH(g, ft_rs_launch, c, P, K, dpol, dkdpart);
+  return -1;
+}
+
+
+}  // namespace hank

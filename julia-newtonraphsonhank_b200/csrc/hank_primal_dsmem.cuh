@@ -32,11 +32,18 @@ __device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uin
                "r"(remote_bar)
                : "memory");
 }
-// Data written by peer CTAs: acquire at cluster scope.  Bounded like mbar_wait.
+// Data written by peer CTAs into THIS CTA's shared memory (st.async + complete_tx).  The wait uses the default
+// CTA-scope acquire, as for TMA loads: shared memory has one copy, and the cluster-scope acquire makes ptxas emit
+// CCTL.IVALL (L1 invalidate-all) after every wait (profiles/r02_notes.md).  -DHANK_ACQUIRE_CLUSTER restores it.
+// Bounded like mbar_wait.
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
+#ifdef HANK_ACQUIRE_CLUSTER
       "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+#else
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+#endif
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");

@@ -1,0 +1,573 @@
+// hank_tangent_rowsplit.cuh — tangent-lane sweeps for FEW lanes: one lane group spread over a
+// thread-block cluster, the asset rows split across the cluster's CTAs.
+//
+// Why: in hank_tangent_tma.cuh a lane group is one CTA, so a pass with fewer lane groups than SMs
+// leaves SMs idle and every busy SM has to pull the whole primal tape of a period (n_e column chunks)
+// through its own L2 port (~43 B/clk/SM): 2.4 / 3.4 us per period and lane at 500x7, whatever the
+// arithmetic.  That is the regime of Newton's inner JVP (K = 1, NewtonRaphson.jl:95), of the 64-lane
+// passes on the large grids, and of every rank of a Jacobian build sharded over 8 GPUs.
+//
+// Here a cluster of NC CTAs carries L lanes; CTA `rank` owns asset rows [rank*NT, (rank+1)*NT) of every
+// income state (one row per thread, all n_e states of the row in that thread's registers, so the Markov
+// mix stays thread-local exactly as in the one-CTA kernels).  Each CTA stages only ITS rows of the tape
+// (n_e*52*NT bytes per period instead of n_e*52*LDA) with cp.async.bulk copies (one per field and
+// column, SASS UBLKCP) into a ring several periods/columns ahead.
+//
+// The only coupling across rows is the interpolation / lottery neighbourhood: a row reads k̇ at its
+// knot indices i, i+1 (backward) or the masses x, y of its source rows (forward), which may live in
+// another CTA of the cluster.  Those values are written to the owner's shared memory and PULLED
+// through distributed shared memory (mapa + ld.shared::cluster; plain ld.shared when the owner is the
+// reader itself).  Hand-shake per exchange group (GC columns): the owner's threads write, one
+// barrier among the compute warps (which drains their shared-memory stores), NC threads
+// `mbarrier.arrive.shared::cluster` on every CTA's `ready` barrier (count NC), readers `try_wait` on
+// their own.  No cluster barrier inside the sweep.  The waits use the default (CTA-scope) acquire, as
+// CUTLASS's ClusterBarrier does: shared memory has a single copy, so nothing has to be invalidated; the
+// cluster-scope acquire makes ptxas emit CCTL.IVALL (L1 invalidate-all), which was 27 % of all stall
+// samples of the first version of these kernels (profiles/r02_notes.md).
+//
+// A dedicated producer warp (warp NT/32) issues the bulk copies; slots are handed back through `empty`
+// mbarriers (one arrival per compute warp).  A bulk copy costs the issuing warp ~60 cycles whatever its
+// size (UBLKCP runs on the uniform datapath, one lane at a time), so the rows of a CTA have to be ONE
+// contiguous piece per exchange group: the kernels read a row-block-major copy of the tape,
+//   backward: [t][rank][e][6 fields x NT doubles | NT ints],   forward: [t][rank][e][4 fields x NT doubles | NT+4 ints],
+// made by k_tape_rowblocks after the primal sweeps (~100 MB moved at 500x7, T=300: tens of microseconds
+// per linearisation), and exchange ṗ between the two sweeps as [t][cluster][rank][e][lane][NT].  With
+// the column-major tape of the one-CTA kernels a period was 49 copies of 512 B per CTA and the producer
+// set the pace at ~3300 cycles per period (profiles/r02_notes.md).
+//
+// Software pipeline: the write stage (A) of group q runs LA groups ahead of its read stage (B), so the
+// DSMEM round trip of one group hides behind the arithmetic of others.  With stage order
+// [A(q), sync, arrive(q), B(q-LA)] a writer that reaches A(q) knows every peer has finished B(q-2LA-2),
+// hence NB = 2LA+2 exchange buffers are enough and no "buffer free" signal is needed.  GC = NE, LA = 0
+// exchanges a whole period at once (fewest hand-shakes: the latency regime); GC = 1, LA = 2 streams
+// column by column (smallest buffers: the large grids).
+//
+// Summation order: the same ascending-source order as gather_row in hank_tangent.cuh for the first two
+// sources of each range; parity with the oracle is at the 1e-10 / 1e-12 bar either way.
+#pragma once
+#include "hank_tangent.cuh"
+#include "hank_tangent_tma.cuh"
+#include "hank_primal_dsmem.cuh"   // map_to_cta, mbar_wait_cluster
+
+namespace hank {
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ double ld_cluster_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+// element `off` (doubles) of an exchange buffer whose copy in this CTA starts at `lbase` (generic
+// pointer) / `sbase` (shared address), read from CTA `owner` of the cluster.  BR: take the plain
+// ld.shared path when the owner is the reader (the throughput shapes: DSMEM moves ~20 B/clk per SM);
+// without it every read goes through mapa + ld.shared::cluster (the latency shapes: no branches).
+template <bool BR>
+__device__ __forceinline__ double pull(const double* lbase, uint32_t sbase, int off, uint32_t owner, uint32_t rank) {
+  if (BR) { if (owner == rank) return lbase[off]; }
+  return ld_cluster_f64(map_to_cta(sbase + (uint32_t)off * 8u, owner));
+}
+
+__host__ __device__ constexpr int ilog2c(int v) { return v <= 1 ? 0 : 1 + ilog2c(v >> 1); }
+
+template <int NT> __host__ __device__ constexpr size_t rs_bw_col_bytes() { return (size_t)BW_NF * NT * 8 + (size_t)NT * 4; }
+template <int NT> __host__ __device__ constexpr size_t rs_fw_tape_col_bytes() { return (size_t)FW_NF * NT * 8 + (size_t)(NT + 4) * 4; }
+template <int NT, int L> __host__ __device__ constexpr size_t rs_fw_col_bytes() { return rs_fw_tape_col_bytes<NT>() + (size_t)L * NT * 8; }
+template <int NT, int L, int GC, int LA>
+constexpr size_t rs_bw_smem(int S) { return (size_t)S * GC * rs_bw_col_bytes<NT>() + (size_t)(2 * LA + 2) * GC * L * NT * 8 + (size_t)(2 * S + 2 * LA + 2) * 8 + 128; }
+template <int NT, int L, int GC, int LA>
+constexpr size_t rs_fw_smem(int S) {
+  return (size_t)S * GC * rs_fw_col_bytes<NT, L>() + (size_t)(2 * LA + 2) * 2 * GC * L * NT * 8 + (size_t)2 * L * (NT / 32) * 8 +
+         (size_t)(2 * S + 2 * LA + 2) * 8 + 128;
+}
+
+// ring / buffer cursor: index and phase parity, advanced without divisions
+struct Cursor {
+  int i = 0, par = 0;
+  __device__ __forceinline__ void next(int n) { if (++i == n) { i = 0; par ^= 1; } }
+};
+
+// ======================================================================================
+// Backward tangent sweep, rows split over a cluster.  Grid = NC * ceil(K / L) CTAs of NT + 32 threads
+// (NT/32 compute warps + the producer warp), cluster (NC,1,1).
+// smem: ring[S][GC][6 fields x NT doubles | NT ints] | kb[NB][GC][L][NT] | full[S] | empty[S] | ready[NB]
+// tape_rs: row-block-major backward tape.  dpol (written): [P][cluster][rank][NE][L][NT].
+// thi (nullable): seed horizons per kThiGroup lanes (hank_ks_jacobian_columns).
+// ======================================================================================
+template <int NE, int NC, int NT, int L, int GC, int LA>
+__global__ void __launch_bounds__(NT + 32, 1)
+k_backward_tangent_rs(const Consts<NE> M, const Tape tp, const unsigned char* __restrict__ tape_rs, int K, int S,
+                      const int* __restrict__ thi, const double* __restrict__ dr, const double* __restrict__ dw,
+                      double* __restrict__ dpol) {
+  static_assert(NE % GC == 0, "exchange groups must tile the columns");
+  static_assert(NT % 32 == 0 && (NT & (NT - 1)) == 0, "NT must be a power of two >= 32");
+  constexpr int LDA = NC * NT, NG = NE / GC, NB = 2 * LA + 2, LOGNT = ilog2c(NT), NW = NT / 32;
+  constexpr int COLB = (int)rs_bw_col_bytes<NT>(), COLD = COLB / 8;   // 52*NT bytes, a multiple of 16
+  constexpr int SLOTD = GC * COLD, KBD = GC * L * NT;
+  constexpr bool BR = L > 1;
+  extern __shared__ __align__(128) unsigned char smem_rs[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_rank();
+  const int cluster = blockIdx.x / NC, ncl = gridDim.x / NC;
+  const int lane0 = cluster * L;
+  const int Pfull = M.P, P = thi ? min(M.P, thi[lane0 / kThiGroup]) : M.P;
+  double* ring = reinterpret_cast<double*>(smem_rs);
+  double* kb = ring + (size_t)S * SLOTD;
+  uint64_t* full = reinterpret_cast<uint64_t*>(kb + (size_t)NB * KBD);
+  uint64_t* empty = full + S;
+  uint64_t* ready = empty + S;
+  const uint32_t kb_s = smem_u32(kb);
+  const int ngroups = P * NG;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
+    for (int b = 0; b < NB; ++b) mbar_init(&ready[b], NC);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  cluster_sync_all();   // every CTA's barriers exist before anyone arrives on them
+
+  if (warp == NW) {
+    // ---- producer warp: group gq = pi*NG + g covers columns [g*GC, (g+1)*GC) of period t = P-1-pi; this CTA's rows
+    // of those columns are one contiguous piece of the row-block-major tape: one bulk copy
+    if (lane == 0) {
+      Cursor cs;
+      int t = P - 1, g = 0;
+      for (int gq = 0; gq < ngroups; ++gq) {
+        if (gq >= S) mbar_wait(&empty[cs.i], cs.par ^ 1);
+        mbar_expect_tx(&full[cs.i], (uint32_t)(GC * COLB));
+        bulk_g2s(ring + (size_t)cs.i * SLOTD, tape_rs + (((size_t)t * NC + rank) * NE + g * GC) * COLB, GC * COLB, &full[cs.i]);
+        cs.next(S);
+        if (++g == NG) { g = 0; --t; }
+      }
+    }
+  } else {
+    double Vd[L][NE];
+#pragma unroll
+    for (int l = 0; l < L; ++l)
+#pragma unroll
+      for (int e = 0; e < NE; ++e) Vd[l][e] = 0.0;
+
+    uint32_t rdy_remote = 0;   // this thread's target CTA's ready[0] (threads 0..NC-1 signal one CTA each)
+    if (tid < NC) rdy_remote = map_to_cta(smem_u32(ready), (uint32_t)tid);
+    Cursor sA, sB, bA, bB;     // tape slot / exchange buffer of the next write (A) and read (B) stage
+    double rho = __ldg(tp.rho + (P > 0 ? P - 1 : 0));
+    double drn[L], dwn[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      const bool on = lane0 + l < K && P > 0;
+      drn[l] = on ? __ldg(dr + (size_t)(lane0 + l) * Pfull + P - 1) : 0.0;
+      dwn[l] = on ? __ldg(dw + (size_t)(lane0 + l) * Pfull + P - 1) : 0.0;
+    }
+    for (int t = P - 1; t >= 0; --t) {
+      const double rho_t = rho;
+      double drl[L], dwl[L];
+#pragma unroll
+      for (int l = 0; l < L; ++l) { drl[l] = drn[l]; dwl[l] = dwn[l]; }
+      if (t > 0) {   // next period's scalars, requested a period ahead
+        rho = __ldg(tp.rho + t - 1);
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+          const bool on = lane0 + l < K;
+          drn[l] = on ? __ldg(dr + (size_t)(lane0 + l) * Pfull + t - 1) : 0.0;
+          dwn[l] = on ? __ldg(dw + (size_t)(lane0 + l) * Pfull + t - 1) : 0.0;
+        }
+      }
+      // ---- ĖV in place of V̇⁺ (registers only)
+#pragma unroll
+      for (int l = 0; l < L; ++l) {
+        double ev[NE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+          double s = 0.0;
+#pragma unroll
+          for (int e2 = 0; e2 < NE; ++e2) s = fma(M.Pi[e][e2], Vd[l][e2], s);
+          ev[e] = s;
+        }
+#pragma unroll
+        for (int e = 0; e < NE; ++e) Vd[l][e] = ev[e];
+      }
+      double* dp_t = dpol + (((size_t)t * ncl + cluster) * NC + rank) * (NE * L * NT) + tid;   // [t][cluster][rank][e][l][NT]
+#pragma unroll
+      for (int st = 0; st < NG + LA; ++st) {
+        // ---- B1: this row's coefficients and knot indices for the columns of group st-LA, then k̇ at the two knots
+        // of every lane, requested before the write stage below so that the DSMEM round trips hide behind it
+        // (with LA = 0 the group is its own look-ahead: B1 has to follow the write stage)
+        double cA[GC], cB[GC], E1[GC], vf[GC], k0[GC][L], k1[GC][L];
+        auto B1 = [&]() {
+          const double* sl = ring + (size_t)sB.i * SLOTD + tid;
+          const double* kr_l = kb + (size_t)bB.i * KBD;
+          const uint32_t kr_s = kb_s + (uint32_t)(bB.i * KBD) * 8u;
+          int i0[GC];
+#pragma unroll
+          for (int ce = 0; ce < GC; ++ce) {
+            cA[ce] = sl[ce * COLD + BW_CA * NT]; cB[ce] = sl[ce * COLD + BW_CB * NT];
+            E1[ce] = sl[ce * COLD + BW_E1 * NT]; vf[ce] = sl[ce * COLD + BW_VF * NT];
+            i0[ce] = reinterpret_cast<const int*>(sl - tid + ce * COLD + BW_NF * NT)[tid];
+          }
+          mbar_wait(&ready[bB.i], bB.par);
+#pragma unroll
+          for (int ce = 0; ce < GC; ++ce) {
+            const int i1 = i0[ce] + 1;
+            const uint32_t o0 = (uint32_t)i0[ce] >> LOGNT, o1 = (uint32_t)i1 >> LOGNT;
+            const int f0 = (i0[ce] & (NT - 1)) + ce * L * NT, f1 = (i1 & (NT - 1)) + ce * L * NT;
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+              k0[ce][l] = pull<BR>(kr_l, kr_s, f0 + l * NT, o0, rank);
+              k1[ce][l] = pull<BR>(kr_l, kr_s, f1 + l * NT, o1, rank);
+            }
+          }
+        };
+        if (LA > 0 && st >= LA) B1();
+        if (st < NG) {   // ---- A: k̇ of this CTA's rows for the columns of group st
+          const double* sl = ring + (size_t)sA.i * SLOTD + tid;
+          double* kw = kb + (size_t)bA.i * KBD + tid;
+          mbar_wait(&full[sA.i], sA.par);
+#pragma unroll
+          for (int ce = 0; ce < GC; ++ce) {
+            const int e = st * GC + ce;
+            const double a1 = sl[ce * COLD + BW_A1 * NT], kr = sl[ce * COLD + BW_KR * NT];
+            const double cw = -(rho_t * M.z[e]);
+#pragma unroll
+            for (int l = 0; l < L; ++l) kw[(ce * L + l) * NT] = fma(a1, Vd[l][e], fma(kr, drl[l], cw * dwl[l]));
+          }
+          named_bar_sync(1, NT);   // all k̇ of the group are in shared memory (BAR drains the stores)
+          if (tid < NC) mbar_arrive_remote(rdy_remote + 8u * bA.i);
+          sA.next(S); bA.next(NB);
+        }
+        if (LA == 0) B1();
+        if (st >= LA) {   // ---- B2: ṗ and V̇
+          const int g = st - LA;
+#pragma unroll
+          for (int ce = 0; ce < GC; ++ce) {
+            const int e = g * GC + ce;
+            const double ze = M.z[e];
+            double* dpc = dp_t + e * L * NT;
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+              const double pd = fma(cA[ce], k0[ce][l], cB[ce] * k1[ce][l]);
+              __stcs(dpc + l * NT, pd);
+              Vd[l][e] = fma(vf[ce], fma(ze, dwl[l], -pd), E1[ce] * drl[l]);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive_local(&empty[sB.i]);   // the tape slot goes back to the producer
+          sB.next(S); bB.next(NB);
+        }
+      }
+    }
+  }
+  __syncwarp();
+  cluster_sync_all();   // peers may still be reading this CTA's last exchange buffer
+}
+
+// ======================================================================================
+// Forward tangent sweep, rows split over a cluster.
+// smem: ring[S][ GC x (4 fields x NT doubles | NT+4 ints) | ṗ [GC][L][NT] ] |
+//       xy[NB][2][GC][L][NT] | red[2][L][NT/32] | full[S] | empty[S] | ready[NB]
+// dkdpart: [K][P][NC] per-CTA partial sums of K̇D.
+// ======================================================================================
+// First two sources of each of the two ranges of a destination row: unconditional loads (clamped index, the caller
+// masks the value) so that the loads of all columns of a group are in flight at once.
+template <int L, int NT, bool BR>
+__device__ __forceinline__ void gather_rs_first(const double* xl, const double* yl, uint32_t xs, uint32_t ys, int s0, int s1,
+                                                int s2, uint32_t rank, double (&xv)[2][L], double (&yv)[2][L]) {
+  constexpr int LOGNT = ilog2c(NT);
+  const int self = (int)(rank << LOGNT);   // an absent source reads (and discards) one of this CTA's own rows
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    const int bx = s1 - s0 > d ? s0 + d : self, by = s2 - s1 > d ? s1 + d : self;
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      xv[d][l] = pull<BR>(xl, xs, l * NT + (bx & (NT - 1)), (uint32_t)bx >> LOGNT, rank);
+      yv[d][l] = pull<BR>(yl, ys, l * NT + (by & (NT - 1)), (uint32_t)by >> LOGNT, rank);
+    }
+  }
+}
+// Sources beyond the second of each range: up to eight more per thread with all loads in flight before the adds,
+// long ranges (the mass piling up at the borrowing constraint) by the whole warp, one row at a time.  Same
+// ascending order as gather_row in hank_tangent.cuh.  Must be called by all 32 lanes of a warp.
+template <int L, int NT, bool BR>
+__device__ __forceinline__ void gather_rs_rest(const double* xl, const double* yl, uint32_t xs, uint32_t ys, int s0, int s1,
+                                               int s2, uint32_t rank, int lane, double (&acc)[L]) {
+  constexpr int LOGNT = ilog2c(NT), U = 2, kSerial = 8;
+  auto px = [&](int l, int b) { return pull<BR>(xl, xs, l * NT + (b & (NT - 1)), (uint32_t)b >> LOGNT, rank); };
+  auto py = [&](int l, int b) { return pull<BR>(yl, ys, l * NT + (b & (NT - 1)), (uint32_t)b >> LOGNT, rank); };
+  const int n1 = s1 - s0, n2 = s2 - s1;
+  const int mx = max(n1, n2) - U;
+  if (!__any_sync(0xffffffffu, mx > 0)) return;
+  const int self = (int)(rank << LOGNT);
+  if (mx > 0 && mx <= kSerial) {
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      double v[kSerial];
+#pragma unroll
+      for (int d = 0; d < kSerial; ++d) v[d] = px(l, U + d < n1 ? s0 + U + d : self);
+#pragma unroll
+      for (int d = 0; d < kSerial; ++d) if (U + d < n1) acc[l] += v[d];
+#pragma unroll
+      for (int d = 0; d < kSerial; ++d) v[d] = py(l, U + d < n2 ? s1 + U + d : self);
+#pragma unroll
+      for (int d = 0; d < kSerial; ++d) if (U + d < n2) acc[l] += v[d];
+    }
+  }
+  unsigned bal = __ballot_sync(0xffffffffu, mx > kSerial);
+  while (bal) {
+    const int src = __ffs(bal) - 1;
+    bal &= bal - 1;
+    const int b0 = __shfl_sync(0xffffffffu, s0, src), b1 = __shfl_sync(0xffffffffu, s1, src),
+              b2 = __shfl_sync(0xffffffffu, s2, src);
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      double v = 0.0;
+      for (int b = b0 + U + lane; b < b1; b += 32) v += px(l, b);
+      for (int b = b1 + U + lane; b < b2; b += 32) v += py(l, b);
+      v = warp_sum(v);
+      if (lane == src) acc[l] += v;
+    }
+  }
+}
+
+template <int NE, int NC, int NT, int L, int GC, int LA>
+__global__ void __launch_bounds__(NT + 32, 1)
+k_forward_tangent_rs(const Consts<NE> M, const unsigned char* __restrict__ tape_rs, int K, int Kp, int S,
+                     const int* __restrict__ thi, const double* __restrict__ zeros, const double* __restrict__ dpol,
+                     int pd_rs, double* __restrict__ dkdpart) {
+  static_assert(NE % GC == 0, "exchange groups must tile the columns");
+  constexpr int LDA = NC * NT, NG = NE / GC, NB = 2 * LA + 2, NW = NT / 32;
+  constexpr int COLB = (int)rs_fw_tape_col_bytes<NT>(), COLD = COLB / 8;   // 36*NT + 16 bytes, a multiple of 16
+  constexpr int ST_OFF = FW_NF * NT;                                       // doubles from the column start
+  constexpr int PD_OFF = GC * COLD;                                        // ṗ [GC][L][NT] follows the GC tape columns
+  constexpr int SLOTD = GC * COLD + GC * L * NT, XYD = GC * L * NT;
+  constexpr bool BR = L > 1;
+  extern __shared__ __align__(128) unsigned char smem_rs[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_rank();
+  const int cluster = blockIdx.x / NC, ncl = gridDim.x / NC;
+  const int lane0 = cluster * L;
+  const int P = M.P;
+  double* ring = reinterpret_cast<double*>(smem_rs);
+  double* xy = ring + (size_t)S * SLOTD;
+  double* red = xy + (size_t)NB * 2 * XYD;
+  uint64_t* full = reinterpret_cast<uint64_t*>(red + 2 * L * NW);
+  uint64_t* empty = full + S;
+  uint64_t* ready = empty + S;
+  const uint32_t xy_s = smem_u32(xy);
+  const int ngroups = P * NG;
+  const int pe = thi ? min(P, thi[lane0 / kThiGroup]) : P;   // ṗ is zero (and unwritten) from period pe on
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
+    for (int b = 0; b < NB; ++b) mbar_init(&ready[b], NC);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  cluster_sync_all();
+
+  if (warp == NW) {
+    // ---- producer warp: the group's tape columns (one piece of the row-block-major tape) and ṗ of the L lanes:
+    // one more piece when the backward sweep of this pass was the row-split one (pd_rs), else GC*L pieces of the
+    // caller's [t][e][Kp][LDA] array (hank_forward_policies)
+    constexpr uint32_t PDB = (uint32_t)(GC * L * NT * 8);
+    Cursor cs;
+    int t = 0, g = 0;
+    for (int gq = 0; gq < ngroups; ++gq) {
+      double* dst = ring + (size_t)cs.i * SLOTD;
+      if (lane == 0) {
+        if (gq >= S) mbar_wait(&empty[cs.i], cs.par ^ 1);
+        mbar_expect_tx(&full[cs.i], (uint32_t)(GC * COLB) + PDB);
+        bulk_g2s(dst, tape_rs + (((size_t)t * NC + rank) * NE + g * GC) * COLB, GC * COLB, &full[cs.i]);
+        if (t >= pe) {   // beyond the seed horizon: zeros (the page holds kZeroBytes)
+          for (uint32_t o = 0; o < PDB; o += kZeroBytes)
+            bulk_g2s(dst + PD_OFF + o / 8, zeros, min(PDB - o, (uint32_t)kZeroBytes), &full[cs.i]);
+        } else if (pd_rs) {
+          bulk_g2s(dst + PD_OFF, dpol + ((((size_t)t * ncl + cluster) * NC + rank) * NE + g * GC) * (L * NT), PDB, &full[cs.i]);
+        }
+      }
+      __syncwarp();
+      if (t < pe && !pd_rs)
+        for (int i = lane; i < GC * L; i += 32) {
+          const int ce = i / L, l = i - ce * L;
+          bulk_g2s(dst + PD_OFF + (size_t)i * NT, dpol + ((((size_t)t * NE + g * GC + ce) * Kp + lane0 + l) * LDA + rank * NT), NT * 8,
+                   &full[cs.i]);
+        }
+      cs.next(S);
+      if (++g == NG) { g = 0; ++t; }
+    }
+  } else {
+    double Dd[L][NE];
+#pragma unroll
+    for (int l = 0; l < L; ++l)
+#pragma unroll
+      for (int e = 0; e < NE; ++e) Dd[l][e] = 0.0;
+    uint32_t rdy_remote = 0;
+    if (tid < NC) rdy_remote = map_to_cta(smem_u32(ready), (uint32_t)tid);
+    Cursor sA, sB, bA, bB;
+    for (int t = 0; t < P; ++t) {
+      double kacc[L];
+#pragma unroll
+      for (int l = 0; l < L; ++l) kacc[l] = 0.0;
+      double pv[NE];
+#pragma unroll
+      for (int st = 0; st < NG + LA; ++st) {
+        // ---- B1: the first sources of this CTA's destination rows for the columns of group st-LA are requested
+        // before the write stage below, so that the DSMEM round trips hide behind it
+        int s0[GC], s1[GC], s2[GC];
+        double xv[GC][2][L], yv[GC][2][L];
+        const double* xr_l = xy + (size_t)bB.i * 2 * XYD;
+        const uint32_t xr_s = xy_s + (uint32_t)(bB.i * 2 * XYD) * 8u;
+        auto B1 = [&]() {   // (with LA = 0 the group is its own look-ahead: B1 has to follow the write stage)
+          const double* slb = ring + (size_t)sB.i * SLOTD;
+#pragma unroll
+          for (int ce = 0; ce < GC; ++ce) {
+            const int* sst = reinterpret_cast<const int*>(slb + ce * COLD + ST_OFF) + tid + 1;
+            s0[ce] = sst[0]; s1[ce] = sst[1]; s2[ce] = sst[2];
+          }
+          mbar_wait(&ready[bB.i], bB.par);
+#pragma unroll
+          for (int ce = 0; ce < GC; ++ce)
+            gather_rs_first<L, NT, BR>(xr_l + ce * L * NT, xr_l + XYD + ce * L * NT, xr_s + (uint32_t)(ce * L * NT) * 8u,
+                                       xr_s + (uint32_t)(XYD + ce * L * NT) * 8u, s0[ce], s1[ce], s2[ce], rank, xv[ce], yv[ce]);
+        };
+        if (LA > 0 && st >= LA) B1();
+        if (st < NG) {   // ---- A: lottery masses ẋ, ẏ of this CTA's rows
+          const double* sl = ring + (size_t)sA.i * SLOTD + tid;
+          double* xw = xy + (size_t)bA.i * 2 * XYD + tid;
+          mbar_wait(&full[sA.i], sA.par);
+#pragma unroll
+          for (int ce = 0; ce < GC; ++ce) {
+            const int e = st * GC + ce;
+            double pd[L];
+#pragma unroll
+            for (int l = 0; l < L; ++l) pd[l] = sl[PD_OFF + (ce * L + l) * NT];
+            const double om = sl[ce * COLD + FW_OM * NT], dco = sl[ce * COLD + FW_DCO * NT], Dn = sl[ce * COLD + FW_D * NT];
+            pv[e] = sl[ce * COLD + FW_P * NT];
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+              const double xd = fma(om, Dd[l][e], dco * pd[l]);
+              xw[(ce * L + l) * NT] = xd;
+              xw[XYD + (ce * L + l) * NT] = Dd[l][e] - xd;
+              kacc[l] = fma(pd[l], Dn, kacc[l]);
+            }
+          }
+          named_bar_sync(1, NT);
+          if (tid < NC) mbar_arrive_remote(rdy_remote + 8u * bA.i);
+          if (st == 0 && t > 0 && tid < L && lane0 + tid < K) {   // the previous period's K̇D share of this CTA
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) s += red[(((t - 1) & 1) * L + tid) * NW + w];
+            dkdpart[((size_t)(lane0 + tid) * P + (t - 1)) * NC + rank] = s;
+          }
+          sA.next(S); bA.next(NB);
+        }
+        if (LA == 0) B1();
+        if (st >= LA) {   // ---- B2: sums, and the rows with more than one source per range
+          const int g = st - LA;
+#pragma unroll
+          for (int ce = 0; ce < GC; ++ce) {
+            const int e = g * GC + ce;
+            double acc[L];
+#pragma unroll
+            for (int l = 0; l < L; ++l) {   // 0 + x0 + y0 + x1 + y1: the order of gather_row's predicated chain
+              const int n1 = s1[ce] - s0[ce], n2 = s2[ce] - s1[ce];
+              double a = n1 > 0 ? xv[ce][0][l] : 0.0;
+              if (n2 > 0) a += yv[ce][0][l];
+              if (n1 > 1) a += xv[ce][1][l];
+              if (n2 > 1) a += yv[ce][1][l];
+              acc[l] = a;
+            }
+            gather_rs_rest<L, NT, BR>(xr_l + ce * L * NT, xr_l + XYD + ce * L * NT, xr_s + (uint32_t)(ce * L * NT) * 8u,
+                                      xr_s + (uint32_t)(XYD + ce * L * NT) * 8u, s0[ce], s1[ce], s2[ce], rank, lane, acc);
+#pragma unroll
+            for (int l = 0; l < L; ++l) Dd[l][e] = acc[l];
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive_local(&empty[sB.i]);
+          sB.next(S); bB.next(NB);
+        }
+      }
+      // ---- Markov mix (in place) and second aggregation term <p_t, Ḋ_t>
+#pragma unroll
+      for (int l = 0; l < L; ++l) {
+        double d[NE];
+#pragma unroll
+        for (int e2 = 0; e2 < NE; ++e2) {
+          double s = 0.0;
+#pragma unroll
+          for (int e = 0; e < NE; ++e) s = fma(M.Pi[e][e2], Dd[l][e], s);
+          d[e2] = s;
+        }
+#pragma unroll
+        for (int e2 = 0; e2 < NE; ++e2) { Dd[l][e2] = d[e2]; kacc[l] = fma(pv[e2], d[e2], kacc[l]); }
+      }
+#pragma unroll
+      for (int l = 0; l < L; ++l) {
+        const double s = warp_sum(kacc[l]);
+        if (lane == 0) red[((t & 1) * L + l) * NW + warp] = s;
+      }
+    }
+    named_bar_sync(1, NT);
+    if (tid < L && lane0 + tid < K && P > 0) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) s += red[(((P - 1) & 1) * L + tid) * NW + w];
+      dkdpart[((size_t)(lane0 + tid) * P + (P - 1)) * NC + rank] = s;
+    }
+  }
+  __syncwarp();
+  cluster_sync_all();
+}
+
+// ======================================================================================
+// Row-block-major copies of the primal tape for the kernels above (see the header comment).
+// One thread per (column, row): the row's coefficients and index / range start.
+// ======================================================================================
+static __global__ void k_tape_rowblocks_bw(const unsigned char* __restrict__ src, unsigned char* __restrict__ dst, int ncols,
+                                    int NE, int LDA, int NT) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)ncols * LDA) return;
+  const int col = (int)(i / LDA), row = (int)(i - (size_t)col * LDA), t = col / NE, e = col - t * NE;
+  const int NC = LDA / NT, rank = row / NT, r = row - rank * NT;
+  const unsigned char* s = src + (size_t)col * ((size_t)BW_NF * LDA * 8 + (size_t)LDA * 4);
+  unsigned char* d = dst + (((size_t)t * NC + rank) * NE + e) * ((size_t)BW_NF * NT * 8 + (size_t)NT * 4);
+#pragma unroll
+  for (int f = 0; f < BW_NF; ++f)
+    reinterpret_cast<double*>(d)[f * NT + r] = reinterpret_cast<const double*>(s)[(size_t)f * LDA + row];
+  reinterpret_cast<int*>(d + (size_t)BW_NF * NT * 8)[r] = reinterpret_cast<const int*>(s + (size_t)BW_NF * LDA * 8)[row];
+}
+static __global__ void k_tape_rowblocks_fw(const unsigned char* __restrict__ src, unsigned char* __restrict__ dst, int ncols,
+                                    int NE, int LDA, int NT) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)ncols * LDA) return;
+  const int col = (int)(i / LDA), row = (int)(i - (size_t)col * LDA), t = col / NE, e = col - t * NE;
+  const int NC = LDA / NT, rank = row / NT, r = row - rank * NT;
+  const unsigned char* s = src + (size_t)col * ((size_t)FW_NF * LDA * 8 + (size_t)(LDA + 4) * 4);
+  unsigned char* d = dst + (((size_t)t * NC + rank) * NE + e) * ((size_t)FW_NF * NT * 8 + (size_t)(NT + 4) * 4);
+#pragma unroll
+  for (int f = 0; f < FW_NF; ++f)
+    reinterpret_cast<double*>(d)[f * NT + r] = reinterpret_cast<const double*>(s)[(size_t)f * LDA + row];
+  const int* st = reinterpret_cast<const int*>(s + (size_t)FW_NF * LDA * 8);
+  int* dt = reinterpret_cast<int*>(d + (size_t)FW_NF * NT * 8);
+  dt[r] = st[row];
+  if (r < 4) dt[NT + r] = st[row + NT];   // the block's range starts overlap the next block's by four entries
+}
+
+}  // namespace hank

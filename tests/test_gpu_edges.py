@@ -58,12 +58,42 @@ def test_lane_counts_and_shapes(n_a, n_e, K):
 
 @pytest.mark.parametrize("switch,n_a,K", [("HANK_NO_TMA", 500, 9), ("HANK_NO_TMA", 1000, 5), ("HANK_NO_CLUSTER", 500, 3),
                                           ("HANK_NO_DSMEM", 500, 3), ("HANK_NO_DSMEM", 1000, 2), ("HANK_NO_WIDE", 500, 700),
-                                          ("HANK_NO_OVERLAP", 500, 5)])
+                                          ("HANK_NO_OVERLAP", 500, 5), ("HANK_NO_ROWSPLIT", 500, 5),
+                                          ("HANK_NO_ROWSPLIT", 1000, 3), ("HANK_NO_ROWSPLIT", 2000, 2)])
 def test_fallback_kernels_agree_with_oracle(switch, n_a, K, monkeypatch):
     """The A/B switches read at hank_ctx_create select the fallback kernels (register-prefetch tangents,
     single-CTA and global-exchange primal sweeps, no 6-lane shape, no side stream): same parity bar."""
     monkeypatch.setenv(switch, "1")
     _compare(n_a, 7, 6, K)
+
+
+@pytest.mark.parametrize("n_a,n_e,T,K", [(200, 7, 9, 1), (200, 7, 9, 18), (500, 7, 12, 1), (500, 7, 12, 13), (500, 3, 8, 18),
+                                         (500, 7, 9, 40), (500, 7, 9, 74), (500, 5, 9, 33), (500, 11, 6, 20),
+                                         (1000, 7, 9, 2), (1000, 7, 9, 14), (1000, 7, 9, 19), (1000, 7, 9, 64), (1000, 11, 7, 61),
+                                         (2000, 11, 7, 3), (2000, 11, 7, 21), (2000, 11, 7, 64), (2000, 7, 30, 37)])
+def test_row_split_cluster_shapes(n_a, n_e, T, K):
+    """Few lanes: the rows of a lane group are split over a thread-block cluster (hank_tangent_rowsplit.cuh): one lane per
+    cluster of 8 CTAs with a whole period per exchange (or column by column at 2000 rows) while the clusters fit one
+    wave, then one lane per cluster of 2 (500 rows) or two lanes per cluster of 4 (1000 / 2000 rows); partially filled
+    last clusters, rings that wrap many times."""
+    _compare(n_a, n_e, T, K)
+
+
+def test_row_split_matches_one_cta_kernels(monkeypatch):
+    """Same pass through the row-split clusters and through the one-CTA kernels (HANK_NO_ROWSPLIT=1)."""
+    s = synthetic(500, 7, 40, 6)
+    out = []
+    for off in (False, True):
+        if off:
+            monkeypatch.setenv("HANK_NO_ROWSPLIT", "1")
+        blk = make_block(s["m"], 40)
+        blk.set_terminal(s["vT"]); blk.set_initial_dist(s["D0"])
+        KD, dKD = blk.block(s["r"], s["w"], s["dr"], s["dw"])
+        out.append((KD, dKD, np.stack([blk.policies(l + 1) for l in range(6)])))
+        blk.close()
+    assert np.array_equal(out[0][0], out[1][0])                       # primal: same kernels
+    assert np.array_equal(out[0][2], out[1][2])                       # backward tangents: same arithmetic per point
+    assert close(out[0][1], out[1][1], rtol=1e-12, atol=1e-14)        # forward: per-CTA partial sums differ in order
 
 
 @pytest.mark.parametrize("n_e", [3, 5, 7, 9, 11])
