@@ -146,6 +146,11 @@ int hank_ks_jvp_dev(hank_ctx* ctx, int K, const double* V, double* JV);
  * J: n x (col_end - col_begin).                                                              */
 int hank_ks_jacobian_columns(hank_ctx* ctx, int col_begin, int col_end, double* J);
 int hank_ks_jacobian_columns_dev(hank_ctx* ctx, int col_begin, int col_end, double* J);
+/* Same for an arbitrary ascending list of 1-based columns (host array): the multi-GPU Jacobian build deals the
+ * periods round-robin over the ranks so that every rank holds the same mix of seed horizons.  J: n x ncols,
+ * device pointer, columns in list order.                                                                     */
+int hank_ks_jacobian_column_list_dev(hank_ctx* ctx, int ncols, const int* cols, double* J);
+int hank_ks_jacobian_column_list(hank_ctx* ctx, int ncols, const int* cols, double* J /* host */);
 
 /* ---- Newton-Raphson driver ------------------------------------------------------------ */
 /* NewtonRaphsonHANK / y_Iteration (NewtonRaphson.jl:27-114) with the sweeps, the residuals and

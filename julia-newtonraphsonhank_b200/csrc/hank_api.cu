@@ -109,13 +109,13 @@ __global__ void k_unit_seeds(int P, int K, const int* __restrict__ lane_col, dou
   if (v == 3) dw[(size_t)l * P + t] = 1.0;
 }
 // Jacobian columns with unit seeds e_col: direct residual terms + household term −K̇D.
-__global__ void k_ks_jac_columns(int P, int col_begin, int ncols, double alpha, double ssKS,
+__global__ void k_ks_jac_columns(int P, const int* __restrict__ col_ids, int ncols, double alpha, double ssKS,
                                  const double* __restrict__ x, const double* __restrict__ Z,
                                  const int* __restrict__ col_lane, const double* __restrict__ dKD, double* J) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ncols * P) return;
   const int c = i / P, t = i - c * P;
-  const int col = col_begin + c, tc = col >> 2, v = col & 3;
+  const int col = col_ids[c], tc = col >> 2, v = col & 3;
   double* o = J + (size_t)c * 4 * P;
   double o0 = 0, o1 = 0, o2 = 0, o3 = 0;
   if (t == tc) { if (v == 0) o0 = 1.0; if (v == 2) o1 = 1.0; if (v == 3) o2 = 1.0; if (v == 1) o3 = 1.0; }
@@ -937,32 +937,31 @@ int hank_ks_fjvp(hank_ctx* c, const double* x, const double* Z, int K, const dou
   return rc;
 }
 
-int hank_ks_jacobian_columns_dev(hank_ctx* c, int col_begin, int col_end, double* J) {
-  CK(cudaSetDevice(c->device));
-  if (!c->linearized) return set_error(c, HANK_ERR_STATE, "hank_ks_jacobian_columns needs a preceding hank_ks_linearize");
+// Jacobian columns `cols` (0-based, ascending) at the linearisation point, written to J in that order.
+static int jacobian_cols_impl(hank_ctx* c, const std::vector<int>& cols, double* J) {
   const int P = c->P, n = 4 * P;
-  if (col_begin < 1 || col_end > n + 1 || col_end <= col_begin) return set_error(c, HANK_ERR_ARG, "bad column range");
-  const int c0 = col_begin - 1, ncols = col_end - col_begin;
-  std::vector<int> lane_col, col_lane(ncols, -1), chunk_cols, thi;
+  const int ncols = (int)cols.size();
+  std::vector<int> lane_col, lane_pos, col_lane(ncols, -1), chunk_cols, thi;
   for (int j = 0; j < ncols; ++j)
-    if (((c0 + j) & 3) >= 2) lane_col.push_back(c0 + j);
+    if ((cols[j] & 3) >= 2) { lane_col.push_back(cols[j]); lane_pos.push_back(j); }
   int Kh = (int)lane_col.size();
   if (Kh > 0) RC(ensure_lanes(c, Kh));
   if (c->jac_idx_cap < ncols) {
     dfree(c->d_jac_idx);
     c->jac_idx_cap = 0;
-    RC(dalloc(c, &c->d_jac_idx, (size_t)2 * ncols));
+    RC(dalloc(c, &c->d_jac_idx, (size_t)3 * ncols));
     c->jac_idx_cap = ncols;
   }
-  int* d_lane_col = c->d_jac_idx; int* d_col_lane = c->d_jac_idx + c->jac_idx_cap;
+  int* d_lane_col = c->d_jac_idx; int* d_col_lane = c->d_jac_idx + c->jac_idx_cap; int* d_col_ids = d_col_lane + c->jac_idx_cap;
+  CK(cudaMemcpyAsync(d_col_ids, cols.data(), ncols * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   const int chunk = Kh > 0 ? c->Kcap : 1;
-  // Y / KS columns first need no sweeps: handled by col_lane = -1. Household lanes go in chunks of
+  // Y / KS columns need no sweeps: handled by col_lane = -1. Household lanes go in chunks of
   // Kcap; each chunk writes the columns it owns.
-  int done_cols = 0;  // columns [c0, c0+done_cols) written
+  int done_cols = 0;  // positions [0, done_cols) of `cols` written
   for (int k0 = 0; k0 < std::max(Kh, 1); k0 += chunk) {
     const int kc = Kh > 0 ? std::min(chunk, Kh - k0) : 0;
-    // column sub-range covered by this chunk: up to (not including) the first column of the next chunk
-    const int col_hi = (k0 + kc < Kh) ? lane_col[k0 + kc] - c0 : ncols;
+    // positions covered by this chunk: up to (not including) the first household column of the next chunk
+    const int col_hi = (k0 + kc < Kh) ? lane_pos[k0 + kc] : ncols;
     const int col_lo = done_cols;
     std::fill(col_lane.begin(), col_lane.end(), -1);
     // Lanes of a chunk run latest seed first.  A unit seed at period s leaves V̇ and ṗ exactly zero after s,
@@ -970,7 +969,7 @@ int hank_ks_jacobian_columns_dev(hank_ctx* c, int col_begin, int col_end, double
     // tangent stages zeros beyond it, and the long CTAs are scheduled ahead of the short ones.
     chunk_cols.assign(lane_col.begin() + k0, lane_col.begin() + k0 + kc);
     std::reverse(chunk_cols.begin(), chunk_cols.end());
-    for (int l = 0; l < kc; ++l) col_lane[chunk_cols[l] - c0] = l;
+    for (int l = 0; l < kc; ++l) col_lane[lane_pos[k0 + kc - 1 - l]] = l;
     if (kc > 0) {
       CK(cudaMemcpyAsync(d_lane_col, chunk_cols.data(), kc * sizeof(int), cudaMemcpyHostToDevice, c->stream));
       CK(cudaMemsetAsync(c->d_dr, 0, (size_t)kc * P * sizeof(double), c->stream));
@@ -997,13 +996,47 @@ int hank_ks_jacobian_columns_dev(hank_ctx* c, int col_begin, int col_end, double
     }
     CK(cudaMemcpyAsync(d_col_lane, col_lane.data() + col_lo, (col_hi - col_lo) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     k_ks_jac_columns<<<nblk((size_t)(col_hi - col_lo) * P), 256, 0, c->stream>>>(
-        P, c0 + col_lo, col_hi - col_lo, c->alpha, c->ssKS, c->d_x, c->d_Z, d_col_lane, c->d_dKD, J + (size_t)col_lo * n);
+        P, d_col_ids + col_lo, col_hi - col_lo, c->alpha, c->ssKS, c->d_x, c->d_Z, d_col_lane, c->d_dKD, J + (size_t)col_lo * n);
     c->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));  // host vectors are reused by the next chunk
     done_cols = col_hi;
   }
   return HANK_OK;
+}
+
+int hank_ks_jacobian_columns_dev(hank_ctx* c, int col_begin, int col_end, double* J) {
+  CK(cudaSetDevice(c->device));
+  if (!c->linearized) return set_error(c, HANK_ERR_STATE, "hank_ks_jacobian_columns needs a preceding hank_ks_linearize");
+  const int n = 4 * c->P;
+  if (col_begin < 1 || col_end > n + 1 || col_end <= col_begin) return set_error(c, HANK_ERR_ARG, "bad column range");
+  std::vector<int> cols(col_end - col_begin);
+  for (int j = 0; j < (int)cols.size(); ++j) cols[j] = col_begin - 1 + j;
+  return jacobian_cols_impl(c, cols, J);
+}
+
+int hank_ks_jacobian_column_list_dev(hank_ctx* c, int ncols, const int* cols1, double* J) {
+  CK(cudaSetDevice(c->device));
+  if (!c->linearized) return set_error(c, HANK_ERR_STATE, "hank_ks_jacobian_column_list needs a preceding hank_ks_linearize");
+  const int n = 4 * c->P;
+  if (ncols < 1 || !cols1) return set_error(c, HANK_ERR_ARG, "empty column list");
+  std::vector<int> cols(ncols);
+  for (int j = 0; j < ncols; ++j) {
+    if (cols1[j] < 1 || cols1[j] > n || (j > 0 && cols1[j] <= cols1[j - 1]))
+      return set_error(c, HANK_ERR_ARG, "column list must be ascending, 1-based and within 1..n");
+    cols[j] = cols1[j] - 1;
+  }
+  return jacobian_cols_impl(c, cols, J);
+}
+
+int hank_ks_jacobian_column_list(hank_ctx* c, int ncols, const int* cols1, double* J) {
+  CK(cudaSetDevice(c->device));
+  const size_t n = (size_t)4 * c->P;
+  if (ncols < 1) return set_error(c, HANK_ERR_ARG, "empty column list");
+  RC(ensure_V(c, ncols));
+  RC(hank_ks_jacobian_column_list_dev(c, ncols, cols1, c->d_JV));
+  CK(cudaMemcpyAsync(J, c->d_JV, n * ncols * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  return check_status(c);
 }
 
 int hank_ks_jacobian_columns(hank_ctx* c, int col_begin, int col_end, double* J) {

@@ -43,7 +43,7 @@
 // column by column (smallest buffers: the large grids).
 //
 // Summation order: the same ascending-source order as gather_row in hank_tangent.cuh for the first two
-// sources of each range; parity with the oracle is at the 1e-10 / 1e-12 bar either way.
+// sources of each range; the parity bar (1e-10 relative / 1e-12 absolute) holds either way.
 #pragma once
 #include "hank_tangent.cuh"
 #include "hank_tangent_tma.cuh"
@@ -314,18 +314,21 @@ __device__ __forceinline__ void gather_rs_rest(const double* xl, const double* y
   const int mx = max(n1, n2) - U;
   if (!__any_sync(0xffffffffu, mx > 0)) return;
   const int self = (int)(rank << LOGNT);
+  // batches of two more sources per range (most rows that get here have three or four), loads before adds; the
+  // x tail is finished before the y tail starts (gather_row's order), so the y batches wait for the x vote
   if (mx > 0 && mx <= kSerial) {
 #pragma unroll
     for (int l = 0; l < L; ++l) {
-      double v[kSerial];
-#pragma unroll
-      for (int d = 0; d < kSerial; ++d) v[d] = px(l, U + d < n1 ? s0 + U + d : self);
-#pragma unroll
-      for (int d = 0; d < kSerial; ++d) if (U + d < n1) acc[l] += v[d];
-#pragma unroll
-      for (int d = 0; d < kSerial; ++d) v[d] = py(l, U + d < n2 ? s1 + U + d : self);
-#pragma unroll
-      for (int d = 0; d < kSerial; ++d) if (U + d < n2) acc[l] += v[d];
+      for (int d = U; d < n1; d += 2) {
+        const double a = px(l, s0 + d), b = px(l, d + 1 < n1 ? s0 + d + 1 : self);
+        acc[l] += a;
+        if (d + 1 < n1) acc[l] += b;
+      }
+      for (int d = U; d < n2; d += 2) {
+        const double a = py(l, s1 + d), b = py(l, d + 1 < n2 ? s1 + d + 1 : self);
+        acc[l] += a;
+        if (d + 1 < n2) acc[l] += b;
+      }
     }
   }
   unsigned bal = __ballot_sync(0xffffffffu, mx > kSerial);

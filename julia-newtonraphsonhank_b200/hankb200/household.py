@@ -241,6 +241,13 @@ class HouseholdBlock:
         self._ck(self._L.hank_ks_jacobian_columns(self._h, int(col_begin), int(col_end), _p(out)))
         return out.T
 
+    def jacobian_column_list(self, cols):
+        """Jacobian columns `cols` (1-based, ascending) at the linearisation point: (n, len(cols))."""
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        out = np.empty((len(cols), self.n))
+        self._ck(self._L.hank_ks_jacobian_column_list(self._h, len(cols), cols.ctypes.data_as(c_ip), _p(out)))
+        return out.T
+
     def newton_solve(self, Jbar, x0, Z, eps=1e-9, eps_inner=1e-9, solver="lu"):
         """NewtonRaphsonHANK on the device. Jbar[i, j] NumPy (n, n)."""
         n = self.n

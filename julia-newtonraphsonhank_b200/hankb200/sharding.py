@@ -21,6 +21,20 @@ def column_partition(n, world):
     return out
 
 
+def period_round_robin(n, world, rank, n_endog=4):
+    """Balanced alternative to column_partition for Jacobian builds: the periods are dealt round-robin, rank r
+    takes all n_endog columns of the periods t with t % world == r (1-based ascending column list).  A unit seed at
+    period s costs a backward sweep of s periods, so contiguous blocks would leave every long sweep on the last
+    rank; dealt this way every rank holds the same mix of seed horizons."""
+    P = n // n_endog
+    return np.array([n_endog * t + v + 1 for t in range(rank, P, world) for v in range(n_endog)], dtype=np.int32)
+
+
+def round_robin_permutation(n, world, n_endog=4):
+    """perm such that J_full[:, perm] = concatenation over ranks of the period_round_robin blocks."""
+    return np.concatenate([period_round_robin(n, world, r, n_endog) - 1 for r in range(world)])
+
+
 def lane_slice(K, world, rank):
     """Lanes [lo, hi) of a K-lane JVP batch owned by `rank`."""
     base, rem = divmod(K, world)
@@ -44,9 +58,18 @@ def gather_columns(local, world, rank, group=None):
     return np.concatenate([bufs[r].numpy()[: widths[r]] for r in range(world)], axis=0).T
 
 
-def jacobian_distributed(blk, n, world, rank, group=None):
+def jacobian_distributed(blk, n, world, rank, group=None, balanced=False):
     """Full (n, n) Jacobian at blk's current linearisation: each rank builds its column block with
-    `blk.jacobian_columns(begin, end)` and the blocks are gathered."""
+    `blk.jacobian_columns(begin, end)` (contiguous blocks) or, with `balanced`, `blk.jacobian_column_list(cols)`
+    for its round-robin periods, and the blocks are gathered (and put back in column order)."""
+    if balanced:
+        cols = period_round_robin(n, world, rank)
+        local = blk.jacobian_column_list(cols) if len(cols) else np.zeros((n, 0))
+        if world == 1:
+            return local
+        J = np.empty((n, n))
+        J[:, round_robin_permutation(n, world)] = gather_columns(local, world, rank, group)
+        return J
     b, e = column_partition(n, world)[rank]
     local = blk.jacobian_columns(b, e) if e > b else np.zeros((n, 0))
     if world == 1:

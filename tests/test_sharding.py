@@ -28,6 +28,10 @@ class OracleBlock:
         g = self.g
         return self.orc.jacobian(self.ks, g["ss_value"], g["ss_D"], np.ones(self.P), g["x0"], np.arange(b - 1, e - 1))
 
+    def jacobian_column_list(self, cols):
+        g = self.g
+        return self.orc.jacobian(self.ks, g["ss_value"], g["ss_D"], np.ones(self.P), g["x0"], np.asarray(cols) - 1)
+
 
 def _worker(rank, world, port, out):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "julia-newtonraphsonhank_b200"))
@@ -38,6 +42,8 @@ def _worker(rank, world, port, out):
     n = 4 * (int(g["T"]) - 1)
     J = jacobian_distributed(OracleBlock(g), n, world, rank)
     np.save(os.path.join(out, f"J{rank}.npy"), J)
+    Jb = jacobian_distributed(OracleBlock(g), n, world, rank, balanced=True)
+    np.save(os.path.join(out, f"Jb{rank}.npy"), Jb)
     dist.destroy_process_group()
 
 
@@ -60,3 +66,21 @@ def test_sharded_jacobian_gloo(tmp_path):
     J0 = np.load(tmp_path / "J0.npy"); J1 = np.load(tmp_path / "J1.npy")
     assert np.array_equal(J0, J1)
     assert J0.shape == g["Jbar"].shape and np.allclose(J0, g["Jbar"], rtol=1e-13, atol=1e-14)
+    # round-robin periods (balanced seed horizons): same matrix after the inverse permutation
+    Jb0 = np.load(tmp_path / "Jb0.npy"); Jb1 = np.load(tmp_path / "Jb1.npy")
+    assert np.array_equal(Jb0, Jb1) and np.array_equal(Jb0, J0)
+
+
+def test_round_robin_rules():
+    from hankb200.sharding import period_round_robin, round_robin_permutation
+    for n, w in ((1196, 8), (116, 2), (28, 3), (8, 4)):
+        blocks = [period_round_robin(n, w, r) for r in range(w)]
+        allc = np.concatenate(blocks)
+        assert sorted(allc.tolist()) == list(range(1, n + 1))
+        assert all(np.all(np.diff(b) > 0) for b in blocks if len(b))
+        sizes = [len(b) for b in blocks]
+        assert max(sizes) - min(sizes) <= 4
+        # every rank holds early and late periods alike: mean seed period within one stride of the others
+        means = [np.mean((b - 1) // 4) for b in blocks if len(b)]
+        assert max(means) - min(means) <= w
+        assert np.array_equal(round_robin_permutation(n, w), allc - 1)
