@@ -31,10 +31,24 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "julia-newtonraphsonhank_b200"))
 
 WORKLOADS = {
-    "ks_500x7_T300": dict(fixture="ss_500x7_T300.npz", desc="Krusell-Smith T=300, 500 assets x 7 income states"),
-    "ks_1000x7_T300": dict(fixture="ss_1000x7_T300.npz", desc="Krusell-Smith T=300, 1000 assets x 7 income states"),
+    "ks_500x7_T300": dict(fixture="ss_500x7_T300.npz", desc="Krusell-Smith T=300, 500 assets x 7 income states (BASELINE configs 2/3)"),
+    "ks_1000x7_T300": dict(fixture="ss_1000x7_T300.npz", desc="Krusell-Smith T=300, 1000 assets x 7 income states (BASELINE config 5: --lanes 64)"),
+    # no steady-state record at this size: synthetic-throughput inputs of SURVEY.md 8d-ii through hank_block (r, w paths + K lanes)
+    "ks_2000x11_T500": dict(shape=(2000, 11, 500), desc="2000 assets x 11 income states, T=500, synthetic-throughput inputs (BASELINE config 4: --lanes 64)"),
 }
 METRIC, UNIT = "jvps_per_sec", "JVP/s"
+
+
+def synthetic_inputs(n_a, n_e, T, rbar=0.015, wbar=1.35, c0=0.1):
+    """Synthetic-throughput regime: closed-form monotone terminal value, uniform D0, smooth paths."""
+    from hankb200 import model as M
+    grid = M.double_exponential(n_a, 0.0, 200.0)
+    z, Pi = M.rouwenhorst_discretization(n_e, 0.966, 0.283)
+    P = T - 1
+    vT = (1 + rbar) * ((rbar * grid[None, :] + wbar * z[:, None]) + c0) ** (-2.0)
+    t = np.arange(1, P + 1)
+    return dict(grid=grid, z=z, Pi=Pi, beta=0.98, gamma=2.0, borrow_cons=0.0, T=T, P=P, n_a=n_a, n_e=n_e, vT=vT,
+                D0=np.full((n_e, n_a), 1.0 / (n_a * n_e)), r=rbar * (1 + 0.1 * 0.9 ** t), w=wbar * (1 + 0.05 * 0.9 ** t))
 
 
 def load_fixture(name):
@@ -103,15 +117,38 @@ class ClockSampler:
 _W = {}
 
 
+def is_synth(workload):
+    return "shape" in WORKLOADS[workload]
+
+
+def workload_inputs(workload):
+    """Fixture-based (Krusell-Smith full function) or synthetic (household block only) inputs of a workload."""
+    if is_synth(workload):
+        sy = synthetic_inputs(*WORKLOADS[workload]["shape"])
+        return dict(sy=sy, T=sy["T"], P=sy["P"], n=4 * sy["P"], n_a=sy["n_a"], n_e=sy["n_e"])
+    return load_fixture(workload)
+
+
 def _ref_worker_init(workload):
     from oracle import oracle as O
-    fx = load_fixture(workload); g = fx["g"]
+    fx = workload_inputs(workload)
     _W["fx"] = fx
-    _W["orc"] = O.Oracle(g["grid"], g["z"], g["Pi"], float(g["beta"]), float(g["gamma"]), float(g["borrow_cons"]), fx["T"])
+    if is_synth(workload):
+        sy = fx["sy"]
+        _W["orc"] = O.Oracle(sy["grid"], sy["z"], sy["Pi"], sy["beta"], sy["gamma"], sy["borrow_cons"], sy["T"])
+    else:
+        g = fx["g"]
+        _W["orc"] = O.Oracle(g["grid"], g["z"], g["Pi"], float(g["beta"]), float(g["gamma"]), float(g["borrow_cons"]), fx["T"])
 
 
 def _ref_worker(V):
-    fx = _W["fx"]; g = fx["g"]
+    fx = _W["fx"]
+    if "sy" in fx:   # household block only: V = (dr, dw)
+        sy = fx["sy"]
+        pol, dpol, _, _ = _W["orc"].backward(sy["vT"], sy["r"], sy["w"], V[0], V[1])
+        KD, dKD = _W["orc"].forward(sy["D0"], pol, dpol)
+        return float(dKD.sum())
+    g = fx["g"]
     F, JV = _W["orc"].ks_fjvp(fx["ks"], g["ss_value"], g["ss_D"], fx["Z"], fx["x0"], V)
     return float(JV.sum())
 
@@ -119,10 +156,12 @@ def _ref_worker(V):
 def make_config(args, world, fx):
     """The workload description both arms print (the reference arm times a bounded sample of it)."""
     alg = 8.0 * fx["n_a"] * fx["n_e"] * fx["P"] * args.lanes
+    step = ("backward + forward sweep of the household block with K tangent lanes (hank_block)" if is_synth(args.workload) else
+            "linearise F(x) (primal sweeps) + K-lane JVP (tangent sweeps) + residual tangents")
     return {"workload": args.workload, "desc": WORKLOADS[args.workload]["desc"], "lanes_per_gpu_per_step": args.lanes,
-            "step": "linearise F(x) (primal sweeps) + K-lane JVP (tangent sweeps) + residual tangents"
-                    + (" + NCCL all-gather of n x K columns" if world > 1 else ""),
-            "l2": "inputs larger than L2 (policy-tangent stream %.2f GB per step vs 126 MB L2)" % (alg / 1e9)}
+            "step": step + (" + NCCL all-gather of n x K columns" if world > 1 else ""),
+            "l2": "inputs larger than L2 (policy-tangent stream %.2f GB per step vs 126 MB L2)" % (alg / 1e9)
+                  if alg > 2.5e8 else "L2 flushed between timed steps (256 MB device memset)"}
 
 
 def run_reference(args):
@@ -135,11 +174,16 @@ def run_reference(args):
     import multiprocessing as mp
     from oracle import oracle as O
     O.build()
-    fx = load_fixture(args.workload)
+    fx = workload_inputs(args.workload)
     procs = max(1, args.cpu_procs or (os.cpu_count() or 1))
     Kc = args.cpu_lanes                      # lanes per process per step
+    if is_synth(args.workload):
+        Kc = max(1, Kc // 8)                 # ~10x the points per lane of the 500 x 7 case
     rng = np.random.default_rng(1234)
-    Vs = [rng.standard_normal((Kc, fx["n"])) for _ in range(procs)]
+    if is_synth(args.workload):
+        Vs = [(rng.standard_normal((Kc, fx["P"])), rng.standard_normal((Kc, fx["P"]))) for _ in range(procs)]
+    else:
+        Vs = [rng.standard_normal((Kc, fx["n"])) for _ in range(procs)]
     with mp.get_context("fork").Pool(procs, initializer=_ref_worker_init, initargs=(args.workload,)) as pool:
         def step():
             pool.map(_ref_worker, Vs, chunksize=1)
@@ -194,14 +238,21 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    fx = load_fixture(args.workload)
-    g = fx["g"]; P, n, K = fx["P"], fx["n"], args.lanes
-    blk = HouseholdBlock(g["grid"], g["z"], g["Pi"], float(g["beta"]), float(g["gamma"]), float(g["borrow_cons"]),
-                         fx["T"], device=local)
+    synth = is_synth(args.workload)
+    fx = workload_inputs(args.workload)
+    P, n, K = fx["P"], fx["n"], args.lanes
+    if synth:
+        sy = fx["sy"]
+        blk = HouseholdBlock(sy["grid"], sy["z"], sy["Pi"], sy["beta"], sy["gamma"], sy["borrow_cons"], sy["T"], device=local)
+        blk.set_terminal(sy["vT"]); blk.set_initial_dist(sy["D0"])
+    else:
+        g = fx["g"]
+        blk = HouseholdBlock(g["grid"], g["z"], g["Pi"], float(g["beta"]), float(g["gamma"]), float(g["borrow_cons"]),
+                             fx["T"], device=local)
+        blk.set_terminal(g["ss_value"]); blk.set_initial_dist(g["ss_D"])
+        blk.ks_configure(*fx["ks"])
     L = blk._L; h = blk.handle
-    blk.set_terminal(g["ss_value"]); blk.set_initial_dist(g["ss_D"])
-    blk.ks_configure(*fx["ks"])
-    blk.reserve_lanes(max(K, n // 2) if world == 1 else K)   # n/2 household lanes for the Jacobian build
+    blk.reserve_lanes(max(K, n // 2) if (world == 1 and not synth) else K)   # n/2 household lanes for the Jacobian build
     if world > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device=dev)
         if rank == 0:
@@ -211,24 +262,44 @@ def main():
 
     # ---- device-resident inputs (value) and pinned host inputs (e2e) ----------------------------
     rng = np.random.default_rng(1234 + rank)
-    Vh = torch.from_numpy(rng.standard_normal((K, n))).pin_memory()
-    xh = torch.from_numpy(fx["x0"].copy()).pin_memory(); Zh = torch.from_numpy(fx["Z"].copy()).pin_memory()
-    Fh = torch.empty(n, dtype=torch.float64).pin_memory(); JVh = torch.empty((K, n), dtype=torch.float64).pin_memory()
-    Vd = Vh.to(dev); xd = xh.to(dev); Zd = Zh.to(dev)
-    Fd = torch.empty(n, dtype=torch.float64, device=dev); JVd = torch.empty((K, n), dtype=torch.float64, device=dev)
-    ALLd = torch.empty((world * K, n), dtype=torch.float64, device=dev) if world > 1 else None
-    torch.cuda.synchronize()
     vp = lambda t: C.c_void_p(t.data_ptr())
     dp = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_double))
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    if synth:
+        rh, wh = pin(sy["r"]), pin(sy["w"])
+        drh, dwh = pin(rng.standard_normal((K, P))), pin(rng.standard_normal((K, P)))
+        KDh = torch.empty(P, dtype=torch.float64).pin_memory(); JVh = torch.empty((K, P), dtype=torch.float64).pin_memory()
+        rd, wd, drd, dwd = rh.to(dev), wh.to(dev), drh.to(dev), dwh.to(dev)
+        KDd = torch.empty(P, dtype=torch.float64, device=dev); JVd = torch.empty((K, P), dtype=torch.float64, device=dev)
+        out_cols = P   # doubles per lane in the gathered block
+        h2d, d2h = 8 * (2 * P + 2 * K * P), 8 * (P + K * P)
+    else:
+        Vh = pin(rng.standard_normal((K, n)))
+        xh = pin(fx["x0"].copy()); Zh = pin(fx["Z"].copy())
+        Fh = torch.empty(n, dtype=torch.float64).pin_memory(); JVh = torch.empty((K, n), dtype=torch.float64).pin_memory()
+        Vd = Vh.to(dev); xd = xh.to(dev); Zd = Zh.to(dev)
+        Fd = torch.empty(n, dtype=torch.float64, device=dev); JVd = torch.empty((K, n), dtype=torch.float64, device=dev)
+        out_cols = n
+        h2d, d2h = 8 * (n * K + n + P), 8 * (n * K + n)
+    ALLd = torch.empty((world * K, out_cols), dtype=torch.float64, device=dev) if world > 1 else None
+    alg = 8.0 * fx["n_a"] * fx["n_e"] * P * K
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if alg <= 2.5e8 else None   # working set below 2 x L2: flush
+    torch.cuda.synchronize()
 
     def step_dev():
-        blk._ck(L.hank_ks_linearize_dev(h, vp(xd), vp(Zd), vp(Fd)))
-        blk._ck(L.hank_ks_jvp_dev(h, K, vp(Vd), vp(JVd)))
+        if synth:
+            blk._ck(L.hank_block_dev(h, vp(rd), vp(wd), K, vp(drd), vp(dwd), vp(KDd), vp(JVd)))
+        else:
+            blk._ck(L.hank_ks_linearize_dev(h, vp(xd), vp(Zd), vp(Fd)))
+            blk._ck(L.hank_ks_jvp_dev(h, K, vp(Vd), vp(JVd)))
         if world > 1:
-            blk._ck(L.hank_allgather_columns_dev(h, vp(JVd), K * n, vp(ALLd)))
+            blk._ck(L.hank_allgather_columns_dev(h, vp(JVd), K * out_cols, vp(ALLd)))
 
     def step_e2e():
-        blk._ck(L.hank_ks_fjvp(h, dp(xh), dp(Zh), K, dp(Vh), dp(Fh), dp(JVh)))
+        if synth:
+            blk._ck(L.hank_block(h, dp(rh), dp(wh), K, dp(drh), dp(dwh), dp(KDh), dp(JVh)))
+        else:
+            blk._ck(L.hank_ks_fjvp(h, dp(xh), dp(Zh), K, dp(Vh), dp(Fh), dp(JVh)))
 
     def barrier():
         torch.cuda.synchronize()
@@ -237,12 +308,20 @@ def main():
         blk.sync()
 
     def timed(fn, steps):
+        """CUDA-event time of `steps` calls on the context's stream, barrier + synchronize on both sides, max over ranks.
+        With the L2 flush each step is timed on its own (the flush is outside the events)."""
         barrier()
         t0 = time.time()
-        blk.timer_start()
-        for _ in range(steps):
-            fn()
-        ms = blk.timer_stop()
+        if flush is None:
+            blk.timer_start()
+            for _ in range(steps):
+                fn()
+            ms = blk.timer_stop()
+        else:
+            ms = 0.0
+            for _ in range(steps):
+                flush.zero_(); torch.cuda.synchronize()
+                blk.timer_start(); fn(); ms += blk.timer_stop()
         blk.sync()
         t1 = time.time()
         barrier()
@@ -271,6 +350,31 @@ def main():
     ms_e2e, _, _ = timed(step_e2e, args.steps)
     e2e_val = world * K * args.steps / (ms_e2e * 1e-3)
 
+    # ---- N > 1: the north star's split — ONE Jacobian's columns over the ranks (strong scaling) ---
+    strong = None
+    if world > 1 and not synth:
+        from hankb200.sharding import period_round_robin
+        cols = period_round_robin(n, world, rank)
+        kmax = max(len(period_round_robin(n, world, r)) for r in range(world))
+        blk.reserve_lanes(kmax)
+        ones_d = torch.ones(P, dtype=torch.float64, device=dev)
+        loc = torch.zeros((kmax, n), dtype=torch.float64, device=dev)
+        allb = torch.empty((world * kmax, n), dtype=torch.float64, device=dev)
+        cptr = cols.ctypes.data_as(C.POINTER(C.c_int))
+
+        def build():
+            blk._ck(L.hank_ks_linearize_dev(h, vp(xd), vp(ones_d), vp(Fd)))
+            blk._ck(L.hank_ks_jacobian_column_list_dev(h, len(cols), cptr, vp(loc)))
+            blk._ck(L.hank_allgather_columns_dev(h, vp(loc), kmax * n, vp(allb)))
+        for _ in range(3):
+            build()
+        nb = max(5, min(args.steps, 20))
+        ms_b, _, _ = timed(build, nb)
+        strong = {"metric": "ms per full Jacobian build (linearise + %d columns + NCCL all-gather)" % n, "ms": ms_b / nb,
+                  "scaling": "strong", "n_gpus": world, "columns": n, "household_lanes_per_rank": int(np.sum((cols - 1) % 4 >= 2)),
+                  "partition": "periods dealt round-robin over the ranks (equal mix of seed horizons)",
+                  "allgather_bytes_per_rank": int(kmax * n * 8), "steps": nb}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -279,7 +383,6 @@ def main():
     # ---- roofline of the dominant kernel (algorithmic bytes: 8*G*P*K per tangent sweep) ----------
     G = fx["n_a"] * fx["n_e"]
     peak, peak_src = peaks()
-    alg = 8.0 * G * P * K
     per = {k: (v[0] / v[1] if v[1] else None) for k, v in kt.items()}
     dom = max(("backward_tangent", "forward_tangent"), key=lambda k: per[k] or 0.0)
     ach = alg / (per[dom] * 1e-3) / 1e9
@@ -291,25 +394,27 @@ def main():
             traffic = per_lane * K if per_lane else None
         except Exception:
             traffic = None
-    tma = fx["n_a"] <= 1024 and os.environ.get("HANK_NO_TMA") != "1"
-    roofline = {"bound": "hbm", "kernel": "k_" + dom + ("_tma" if tma else ""), "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+    roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
                 "kernel_ms_per_launch": per,
                 "frac_by_kernel": {k: alg / (per[k] * 1e-3) / 1e9 / peak for k in ("backward_tangent", "forward_tangent")},
-                "sweep_pair_GBps": 2 * alg / ((per["backward_tangent"] + per["forward_tangent"]) * 1e-3) / 1e9}
+                "sweep_pair_GBps": 2 * alg / ((per["backward_tangent"] + per["forward_tangent"]) * 1e-3) / 1e9,
+                "us_per_period": {k: 1e3 * v / P for k, v in per.items() if v}}
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": make_config(args, world, fx),
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(8 * (n * K + n + P)),
-                "d2h_bytes_per_step": int(8 * (n * K + n)), "ms_per_step": ms_e2e / args.steps},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
     }
+    if strong:
+        out["jacobian_build_strong_scaling"] = strong
 
-    # ---- extras at N = 1: Jacobian build, Newton solve, CPU baseline ------------------------------
-    if world == 1 and not args.no_newton:
+    # ---- N = 1: the metric's other halves — Jacobian build and ms per Newton solve, CPU beside them ---
+    if world == 1 and not synth and not args.no_newton:
         ones = np.ones(P)
         blk.linearize(fx["x0"], ones)
         Jd = torch.empty((n, n), dtype=torch.float64, device=dev)
@@ -320,37 +425,59 @@ def main():
             blk._ck(L.hank_ks_jacobian_columns_dev(h, 1, n + 1, vp(Jd)))
             jac_ms = min(jac_ms, blk.timer_stop())
         Jbar = Jd.cpu().numpy().T.copy()   # device buffer is column-major
-        tw = time.perf_counter()
-        x, st = blk.newton_solve(Jbar, fx["x0"], fx["Z"], solver="lu")
-        newton_ms = 1e3 * (time.perf_counter() - tw)
-        tw = time.perf_counter()
-        x, st = blk.newton_solve(Jbar, fx["x0"], fx["Z"], solver="lu")
-        newton_ms = min(newton_ms, 1e3 * (time.perf_counter() - tw))
-        nb_ms = 1e9
-        for _ in range(2):
-            tw = time.perf_counter()
-            xb, stb = blk.newton_solve(Jbar, fx["x0"], fx["Z"], solver="lu_batched")
-            nb_ms = min(nb_ms, 1e3 * (time.perf_counter() - tw))
+
+        def newton_timed(solver, reps):
+            """CUDA-event time on the context's stream around hank_newton_solve (host buffers in and out)."""
+            best, res = 1e9, None
+            for _ in range(reps):
+                blk.sync(); blk.timer_start()
+                res = blk.newton_solve(Jbar, fx["x0"], fx["Z"], solver=solver)
+                best = min(best, blk.timer_stop())
+            return best, res
+        newton_ms, (x, st) = newton_timed("lu", 2)
+        nb_ms, (xb, stb) = newton_timed("lu_batched", 3)
         Fx = blk.linearize(x, fx["Z"])
         out["jacobian_build"] = {"ms": jac_ms, "columns": n, "household_lanes": n // 2,
                                  "note": "full n x n sequence-space Jacobian by unit-seed lanes at a given linearisation (min of 3); "
                                          "Y/KS columns skip the sweeps"}
-        out["newton"] = {"ms_per_solve": newton_ms, "solver": "lu", "outer": st["outer"], "jvps": st["jvps"],
-                         "inner": st["inner"], "jvps_per_sec_k1": st["jvps"] / (newton_ms * 1e-3),
-                         "residual_norm": float(np.linalg.norm(Fx)), "timing": "host wall clock around hank_newton_solve (min of 2)",
+        out["newton"] = {"metric": "ms per Newton solve (KS T=%d, %d x %d)" % (fx["T"], fx["n_a"], fx["n_e"]),
+                         "ms_per_solve": newton_ms, "solver": "lu (exact preconditioner solve), one single-lane JVP sweep pair per inner iteration "
+                                                              "as in NewtonRaphson.jl:94-105",
+                         "outer": st["outer"], "jvps": st["jvps"], "inner": st["inner"], "jvps_per_sec_k1": st["jvps"] / (newton_ms * 1e-3),
+                         "ms_per_inner_iteration": newton_ms / max(st["jvps"], 1),
+                         "residual_norm": float(np.linalg.norm(Fx)), "timing": "CUDA events on the context's stream around hank_newton_solve (min of 2)",
                          "batched_jacobian_mode": {"ms_per_solve": nb_ms, "outer": stb["outer"], "inner": stb["inner"],
                                                    "max_abs_diff_vs_sequential": float(np.max(np.abs(xb - x))),
                                                    "note": "J(x) assembled once per outer iteration from unit-seed lanes; inner J(x)y by FP64 GEMV"}}
+        if not args.no_cpu:
+            from oracle import oracle as O
+            O.build()
+            orc = O.Oracle(g["grid"], g["z"], g["Pi"], float(g["beta"]), float(g["gamma"]), float(g["borrow_cons"]), fx["T"])
+            tw = time.perf_counter()
+            xo, so = orc.newton(fx["ks"], g["ss_value"], g["ss_D"], fx["Z"], Jbar, fx["x0"], solver="lu")
+            dtn = time.perf_counter() - tw
+            out["newton"]["cpu_baseline"] = {"ms_per_solve": 1e3 * dtn, "cores": 1, "kind": "port", "outer": so["outer"], "inner": so["inner"],
+                                             "sample": "the whole solve, same Jbar, same x0 and shock, LU preconditioner solve",
+                                             "max_abs_diff_gpu_vs_cpu_path": float(np.max(np.abs(x - xo))),
+                                             "speedup_sequential": 1e3 * dtn / newton_ms, "speedup_batched": 1e3 * dtn / nb_ms}
     if world == 1 and not args.no_cpu:
         from oracle import oracle as O
         O.build()
-        orc = O.Oracle(g["grid"], g["z"], g["Pi"], float(g["beta"]), float(g["gamma"]), float(g["borrow_cons"]), fx["T"])
-        Kc = args.cpu_lanes
-        Vc = Vh.numpy()[:Kc]
-        orc.ks_fjvp(fx["ks"], g["ss_value"], g["ss_D"], fx["Z"], fx["x0"])  # warm-up (primal only)
-        tw = time.perf_counter()
-        Fc, JVc = orc.ks_fjvp(fx["ks"], g["ss_value"], g["ss_D"], fx["Z"], fx["x0"], Vc)
-        dtc = time.perf_counter() - tw
+        Kc = args.cpu_lanes if not synth else max(1, args.cpu_lanes // 8)
+        if synth:
+            orc = O.Oracle(sy["grid"], sy["z"], sy["Pi"], sy["beta"], sy["gamma"], sy["borrow_cons"], sy["T"])
+            orc.backward(sy["vT"], sy["r"], sy["w"])   # warm-up (primal only)
+            tw = time.perf_counter()
+            pol, dpol, _, _ = orc.backward(sy["vT"], sy["r"], sy["w"], drh.numpy()[:Kc], dwh.numpy()[:Kc])
+            _, JVc = orc.forward(sy["D0"], pol, dpol)
+            dtc = time.perf_counter() - tw
+        else:
+            orc = O.Oracle(g["grid"], g["z"], g["Pi"], float(g["beta"]), float(g["gamma"]), float(g["borrow_cons"]), fx["T"])
+            Vc = Vh.numpy()[:Kc]
+            orc.ks_fjvp(fx["ks"], g["ss_value"], g["ss_D"], fx["Z"], fx["x0"])  # warm-up (primal only)
+            tw = time.perf_counter()
+            Fc, JVc = orc.ks_fjvp(fx["ks"], g["ss_value"], g["ss_D"], fx["Z"], fx["x0"], Vc)
+            dtc = time.perf_counter() - tw
         # the CPU sample doubles as an in-run parity check of the GPU result
         err = float(np.max(np.abs(JVh.numpy()[:Kc] - JVc) / (1e-12 * max(1.0, np.abs(JVc).max()) + 1e-10 * np.abs(JVc))))
         out["cpu_baseline"] = {"value": Kc / dtc, "unit": UNIT, "cores": 1, "kind": "port",

@@ -172,6 +172,8 @@ int hank_comm_init(hank_ctx* ctx, int nranks, int rank, const void* id128);
 /* All-gather equal-sized column blocks: every rank contributes count doubles (device pointer)
  * and receives nranks*count in rank order.                                                    */
 int hank_allgather_columns_dev(hank_ctx* ctx, const double* local, size_t count, double* all);
+/* Same with HOST buffers (synchronous): what a Julia process holding its column block in a Matrix calls.       */
+int hank_allgather_columns(hank_ctx* ctx, const double* local, size_t count, double* all);
 int hank_comm_destroy(hank_ctx* ctx);
 
 #ifdef __cplusplus

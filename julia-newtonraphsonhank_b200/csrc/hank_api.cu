@@ -433,7 +433,7 @@ void hank_ctx_destroy(hank_ctx* c) {
   dfree(c->d_jac_idx); dfree(c->d_thi); dfree(c->d_zero); dfree(c->d_xch); dfree(c->d_kdpart); dfree(c->d_KD); dfree(c->d_dkdpart); dfree(c->d_dKD); dfree(c->d_status);
   dfree(c->d_x); dfree(c->d_Z); dfree(c->d_F); dfree(c->d_V); dfree(c->d_JV);
   dfree(c->d_Jinv); dfree(c->d_newton); dfree(c->d_newton_i); dfree(c->d_lu_work);
-  dfree(c->tape_rs_bw); dfree(c->tape_rs_fw);
+  dfree(c->tape_rs_bw); dfree(c->tape_rs_fw); dfree(c->d_gather);
   for (auto& r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   if (c->h_status) cudaFreeHost(c->h_status);

@@ -100,6 +100,30 @@ int hank_allgather_columns_dev(hank_ctx* c, const double* local, size_t count, d
   return HANK_OK;
 }
 
+// Host-pointer form: the block is staged through the context's pinned / device scratch, gathered, and copied back.
+int hank_allgather_columns(hank_ctx* c, const double* local, size_t count, double* all) {
+  if (!c || !local || !all) return HANK_ERR_ARG;
+  int rc = hank::cuda_check(c, cudaSetDevice(c->device), "cudaSetDevice");
+  if (rc) return rc;
+  const size_t need = (size_t)(c->nranks + 1) * count * sizeof(double);
+  if (c->gather_bytes < need) {
+    if (c->d_gather) cudaFree(c->d_gather);
+    c->d_gather = nullptr; c->gather_bytes = 0;
+    rc = hank::cuda_check(c, cudaMalloc((void**)&c->d_gather, need), "cudaMalloc");
+    if (rc) return rc;
+    c->gather_bytes = need;
+  }
+  double* d_loc = c->d_gather; double* d_all = c->d_gather + count;
+  rc = hank::cuda_check(c, cudaMemcpyAsync(d_loc, local, count * sizeof(double), cudaMemcpyHostToDevice, c->stream), "cudaMemcpyAsync");
+  if (rc) return rc;
+  rc = hank_allgather_columns_dev(c, d_loc, count, d_all);
+  if (rc) return rc;
+  rc = hank::cuda_check(c, cudaMemcpyAsync(all, d_all, (size_t)c->nranks * count * sizeof(double), cudaMemcpyDeviceToHost, c->stream),
+                        "cudaMemcpyAsync");
+  if (rc) return rc;
+  return hank::cuda_check(c, cudaStreamSynchronize(c->stream), "cudaStreamSynchronize");
+}
+
 int hank_comm_destroy(hank_ctx* c) {
   if (!c) return HANK_ERR_ARG;
   if (c->nccl_comm) {

@@ -53,6 +53,7 @@ struct hank_ctx {
 
   // NCCL
   void* nccl_comm = nullptr;
+  double* d_gather = nullptr; size_t gather_bytes = 0;   // scratch of the host-pointer all-gather
   int nranks = 1, rank = 0;
 
   std::string err;

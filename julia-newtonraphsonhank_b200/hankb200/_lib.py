@@ -57,6 +57,7 @@ SIGNATURES = {
     "hank_comm_unique_id": (C.c_int, [C.c_void_p]),
     "hank_comm_init": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_void_p]),
     "hank_allgather_columns_dev": (C.c_int, [ctx_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "hank_allgather_columns": (C.c_int, [ctx_p, c_dp, C.c_size_t, c_dp]),
     "hank_comm_destroy": (C.c_int, [ctx_p]),
 }
 

@@ -1,209 +1,312 @@
-# HankB200.jl — Julia host glue over libhankb200.so (include/hankb200.h).
+# HankB200.jl — Julia host glue over libhankb200.so (include/hankb200.h): a DROP-IN for the hot path of
+# vasudeva-ram/Julia-NewtonRaphsonHANK.
 #
-# NOT EXECUTED IN THIS REPOSITORY'S CI: Julia is not installed in the build image (SURVEY.md §0.7),
-# so this file is written against the C header and the reference's call signatures and is checked
-# only by review; the same entry points are exercised from Python (hankb200/) by the GPU tests.
+# NOT EXECUTED IN THIS REPOSITORY: Julia is not installed in the build image (SURVEY.md §0.7), so this file is written
+# against the C header and the reference's call signatures and is checked by review only; the same C entry points
+# are exercised from Python (hankb200/) by the GPU tests.  INTEGRATION.md §2 lists every deviation from the reference.
 #
-# Usage inside the reference repository (after its own `include`s, see INTEGRATION.md):
+# Usage: `include` it in `Main` AFTER the reference's own files (RunMain.jl:1-9 / test_SteadyState.jl:11-18):
 #
-#     include("HankB200.jl"); using .HankB200
-#     mod = build_model_from_yaml("KrusellSmith.yaml")
-#     ss, _ = get_SteadyStates(mod)
-#     blk = HankB200.HouseholdBlock(mod, ss, ss)            # one hank_ctx on GPU 0
-#     J̅  = HankB200.jacobian(blk, x_ss, exog_ss)           # brute-force JVP columns (config 3)
-#     x  = HankB200.NewtonRaphsonHANK(x_0, J̅, exog_paths, blk)
+#     include("GeneralStructures.jl"); …; include("NewtonRaphson.jl")
+#     include("/path/to/julia-newtonraphsonhank_b200/julia/HankB200.jl")
 #
-# The methods below keep the reference's names and argument meaning:
-#   BackwardIteration(xVec_endog, exog_paths, model, ss_end)   BackwardIteration.jl:46-49
-#   ForwardIteration(policy_seqs, model, ss_initial)           ForwardIteration.jl:253-255
-#   JVP(func, primal, tangent)                                 GeneralStructures.jl:542-544
-#   NewtonRaphsonHANK(x_0, J̅, exog_paths, mod, ss0, ssT; ε)    NewtonRaphson.jl:27-33
-module HankB200
+# Nothing else changes in the caller.  The file adds METHODS to the reference's own generic functions, each with the
+# reference's positional signature and a first argument (or steady-state argument) typed one step more specifically, so
+# that Julia's dispatch picks them for `Float64` / `ForwardDiff.Dual{…,Float64,N}` inputs and the reference's
+# untyped methods stay available as the fallback (`invoke`) for anything the device path does not cover:
+#
+#   BackwardIteration(xVec_endog, exog_paths::NamedTuple, model::SequenceModel, ss_end)      BackwardIteration.jl:46-49
+#   ForwardIteration(policy_seqs::NamedTuple, model::SequenceModel, ss_initial)              ForwardIteration.jl:253-255
+#   NewtonRaphsonHANK(x_0, J̅::SparseMatrixCSC, exog_paths, mod, ss_initial, ss_ending; ε)    NewtonRaphson.jl:27-33
+#   get_xVals(asm::SSAssembler, p_vec)                                                       SteadyState.jl:111-154
+#   ValueFunction(value_next, xVals, model)  (the `value_fn` plug-in)                        KrusellSmith.jl:43-83
+#
+# `JVP(func, primal, tangent)` (GeneralStructures.jl:542-550) and `y_Iteration.fullFunction` (NewtonRaphson.jl:77-83)
+# are NOT redefined: they call `BackwardIteration` / `ForwardIteration` on `Vector{Dual{Tag,Float64,1}}` and therefore
+# reach the device through the methods below unchanged.  `JVP(func, primal, tangents::AbstractMatrix)` is an
+# additional batched method (K lanes per pass; ForwardDiff itself never carries more than 12, prelude.jl:1-11).
+#
+# The device path covers the Krusell-Smith household block (`model.value_fn === ValueFunction`, heterogeneity
+# `(wealth, productivity)`, one heterogeneous variable `KD`); `HankB200.ENABLED[] = false` or any other model
+# falls back to the reference's Julia code.
 
-using LinearAlgebra, SparseArrays
-import ForwardDiff
-
+module HankB200Lib
 const LIB = get(ENV, "HANKB200_LIB", joinpath(@__DIR__, "..", "lib", "libhankb200.so"))
-
 struct HankError <: Exception
     code::Cint
     msg::String
 end
 Base.showerror(io::IO, e::HankError) = print(io, "hankb200 status $(e.code): $(e.msg)")
+last_error(ctx) = unsafe_string(ccall((:hank_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx))
+# status -> exception, like the reference's error(...) / DomainError / ArgumentError (find_ss's line search
+# catches them, SteadyState.jl:199-207)
+check(ctx, rc) = rc == 0 ? nothing : throw(HankError(rc, last_error(ctx)))
+end # module HankB200Lib
 
-mutable struct HouseholdBlock
+module HankB200
+const ENABLED = Ref(true)          # false: every call goes to the reference's Julia code
+const DEVICE = Ref(0)              # CUDA device of the contexts created from here on
+const NEWTON_SOLVER = Ref(:gmres)  # :gmres = the reference's restarted GMRES(20) preconditioner solve (IterativeSolvers
+                                   # defaults); :lu = exact solve with a cached LU of J̅; :lu_batched = as :lu with J(x)
+                                   # assembled once per outer iteration from batched unit-seed lanes
+end
+
+using LinearAlgebra, SparseArrays
+import ForwardDiff
+import .HankB200Lib: LIB, HankError, check
+
+# ── one device context per SequenceModel (created on first use, destroyed by the finalizer) ──────────────────────
+mutable struct HankBlock
     ctx::Ptr{Cvoid}
     n_a::Int; n_e::Int; T::Int; P::Int
-    function HouseholdBlock(ctx, n_a, n_e, T)
-        b = new(ctx, n_a, n_e, T, T - 1)
+    ir::Int; iw::Int; n_endog::Int          # rows of r and w in reshape(x, n_endog, P)
+    terminal_id::UInt; initial_id::UInt     # objectid of the steady-state records last uploaded
+    K::Int                                  # lanes of the last hank_backward
+end
+const _BLOCKS = IdDict{Any,HankBlock}()
+
+_is_ks(model::SequenceModel) = HankB200.ENABLED[] && model.value_fn === ValueFunction &&
+    keys(model.heterogeneity) == (:wealth, :productivity) && vars_of_type(model, :heterogeneous) == (:KD,)
+
+function _block(model::SequenceModel)
+    get!(_BLOCKS, model) do
+        w = model.heterogeneity.wealth; pr = model.heterogeneity.productivity
+        p = model.params; T = model.compspec.T
+        ref = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:hank_ctx_create, LIB), Cint,
+                   (Ref{Ptr{Cvoid}}, Cint, Cint, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Float64),
+                   ref, HankB200.DEVICE[], w.n, pr.n, T, collect(Float64, w.grid), collect(Float64, pr.grid),
+                   Matrix{Float64}(pr.transition), p.β, p.γ, p.borrow_cons)
+        if rc != 0
+            msg = ref[] == C_NULL ? "context allocation failed" : HankB200Lib.last_error(ref[])
+            ref[] == C_NULL || ccall((:hank_ctx_destroy, LIB), Cvoid, (Ptr{Cvoid},), ref[])
+            throw(HankError(rc, msg))
+        end
+        endog = vars_of_type(model, :endogenous)          # r and w are looked up BY NAME (KrusellSmith.jl:53-54)
+        b = HankBlock(ref[], w.n, pr.n, T, T - 1, findfirst(==(:r), endog), findfirst(==(:w), endog), length(endog), 0, 0, 0)
         finalizer(x -> ccall((:hank_ctx_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.ctx), b)
         b
     end
 end
-
-last_error(ctx) = unsafe_string(ccall((:hank_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx))
-check(b::HouseholdBlock, rc) = rc == 0 ? nothing : throw(HankError(rc, last_error(b.ctx)))
-
-"""
-    HouseholdBlock(model::SequenceModel, ss_initial, ss_ending; device = 0)
-
-Creates the device context from the fields `ValueFunction` reads on every call
-(KrusellSmith.jl:44-52) and uploads the two steady-state records' `.value` / `.D`
-(SteadyState.jl:21-27).  `Π` is passed as stored (column-major, row-stochastic).
-"""
-function HouseholdBlock(model, ss_initial, ss_ending; device::Integer = 0)
-    w = model.heterogeneity.wealth; pr = model.heterogeneity.productivity
-    p = model.params; T = model.compspec.T
-    ref = Ref{Ptr{Cvoid}}(C_NULL)
-    rc = ccall((:hank_ctx_create, LIB), Cint,
-               (Ref{Ptr{Cvoid}}, Cint, Cint, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Float64),
-               ref, device, w.n, pr.n, T, collect(Float64, w.grid), collect(Float64, pr.grid),
-               Matrix{Float64}(pr.transition), p.β, p.γ, p.borrow_cons)
-    if rc != 0
-        msg = ref[] == C_NULL ? "context allocation failed" : last_error(ref[])
-        ref[] == C_NULL || ccall((:hank_ctx_destroy, LIB), Cvoid, (Ptr{Cvoid},), ref[])
-        throw(HankError(rc, msg))
-    end
-    b = HouseholdBlock(ref[], w.n, pr.n, T)
-    check(b, ccall((:hank_set_terminal, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), b.ctx, Matrix{Float64}(ss_ending.value)))
-    check(b, ccall((:hank_set_initial_dist, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), b.ctx, Vector{Float64}(ss_initial.D)))
-    check(b, ccall((:hank_ks_configure, LIB), Cint, (Ptr{Cvoid}, Float64, Float64, Float64), b.ctx, p.α, p.δ, ss_initial.vars.KS))
-    b
+function _set_terminal!(b::HankBlock, ss_end)
+    objectid(ss_end) == b.terminal_id && return
+    check(b.ctx, ccall((:hank_set_terminal, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), b.ctx, Matrix{Float64}(ss_end.value)))
+    b.terminal_id = objectid(ss_end)
+end
+function _set_initial!(b::HankBlock, model, ss_initial)
+    objectid(ss_initial) == b.initial_id && return
+    check(b.ctx, ccall((:hank_set_initial_dist, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), b.ctx, Vector{Float64}(ss_initial.D)))
+    p = model.params   # constants of the compiled KS residuals + the lag padding column (GeneralStructures.jl:350-354)
+    check(b.ctx, ccall((:hank_ks_configure, LIB), Cint, (Ptr{Cvoid}, Float64, Float64, Float64), b.ctx, p.α, p.δ, ss_initial.vars.KS))
+    b.initial_id = objectid(ss_initial)
 end
 
-# ── Dual packing: Vector{Dual{T,Float64,N}} is bit-compatible with an (N+1) x len Float64 matrix,
-#    value first (ForwardDiff.jl/src/dual.jl:14-16, partials.jl:1-3) ────────────────────────────
-unpack(v::AbstractVector{Float64}) = (Vector{Float64}(v), Matrix{Float64}(undef, length(v), 0))
-function unpack(v::AbstractVector{ForwardDiff.Dual{Tg,Float64,N}}) where {Tg,N}
-    raw = reinterpret(reshape, Float64, collect(v))          # (N+1) x len
-    (Vector{Float64}(raw[1, :]), Matrix{Float64}(permutedims(raw[2:end, :])))   # len x N
+# ── Dual packing: Vector{Dual{T,Float64,N}} is bit-compatible with an (N+1) x len Float64 matrix, value first
+#    (ForwardDiff.jl/src/dual.jl:14-16, partials.jl:1-3) ─────────────────────────────────────────────────────────
+const HankReal = Union{Float64,ForwardDiff.Dual{<:Any,Float64}}
+_unpack(v::AbstractVector{Float64}) = (Vector{Float64}(v), Matrix{Float64}(undef, length(v), 0))
+function _unpack(v::AbstractVector{ForwardDiff.Dual{Tg,Float64,N}}) where {Tg,N}
+    raw = reinterpret(reshape, Float64, collect(v))                               # (N+1) x len
+    (Vector{Float64}(raw[1, :]), Matrix{Float64}(permutedims(raw[2:end, :])))     # len x N
 end
-repack(::Type{Float64}, val, part) = val
-function repack(::Type{ForwardDiff.Dual{Tg,Float64,N}}, val::AbstractVector, part::AbstractMatrix) where {Tg,N}
+_repack(::Type{Float64}, val, part) = val
+_repack(::Type{ForwardDiff.Dual{Tg,Float64,N}}, val::AbstractArray, part::AbstractMatrix) where {Tg,N} =
     [ForwardDiff.Dual{Tg}(val[i], ForwardDiff.Partials(ntuple(k -> part[i, k], Val(N)))) for i in eachindex(val)]
-end
 
-"""Device handle returned by `BackwardIteration`; `Array(h)` materialises the `Vector{Matrix}` of
-policies for callers that need host matrices (SteadyStateJacobian.jl:226-229)."""
-struct DevicePolicies{TF}
-    blk::HouseholdBlock
+"""
+`policy_seqs.KD` as returned by the device `BackwardIteration`: an `AbstractVector{Matrix{TF}}` whose matrices stay on
+the GPU; `h[t]` (or `collect(h)`) materialises period t for callers that need host matrices
+(SteadyStateJacobian.jl:226-229, SteadyState.jl:225), `ForwardIteration` consumes it without a transfer.
+"""
+struct DevicePolicies{TF} <: AbstractVector{Matrix{TF}}
+    blk::HankBlock
     K::Int
 end
-function Base.Array(h::DevicePolicies{Float64})
-    b = h.blk
-    map(1:b.P) do t
-        out = Matrix{Float64}(undef, b.n_a, b.n_e)
-        check(b, ccall((:hank_get_policy, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}), b.ctx, t, 0, out))
-        out
+Base.size(h::DevicePolicies) = (h.blk.P,)
+function Base.getindex(h::DevicePolicies{TF}, t::Int) where {TF}
+    b = h.blk; G = b.n_a * b.n_e
+    val = Vector{Float64}(undef, G); part = Matrix{Float64}(undef, G, h.K)
+    check(b.ctx, ccall((:hank_get_policy, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}), b.ctx, t, 0, val))
+    for k in 1:h.K
+        check(b.ctx, ccall((:hank_get_policy, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}), b.ctx, t, k, view(part, :, k)))
     end
+    reshape(_repack(TF, val, part), b.n_a, b.n_e)
 end
 
 """
-    BackwardIteration(xVec_endog, exog_paths, blk::HouseholdBlock, ss_end) -> (KD = DevicePolicies,)
+    BackwardIteration(xVec_endog, exog_paths::NamedTuple, model::SequenceModel, ss_end)
 
-Same meaning as BackwardIteration.jl:46-116.  Only `r` and `w` enter the KS household block
-(KrusellSmith.jl:53-54): rows 3 and 4 of `reshape(x, n_endog, T-1)`.
+BackwardIteration.jl:46-116 on the device (`hank_backward`): the reference's signature with `xVec_endog` restricted to
+`Float64` / `Dual{…,Float64,N}` element types.  Only `r` and `w` enter the KS household block (KrusellSmith.jl:53-54).
+Returns `(KD = DevicePolicies,)` — same key, same indexing as the reference's `NamedTuple{het}(Vector{Matrix})`.
 """
-function BackwardIteration(xVec_endog::AbstractVector{TF}, exog_paths::NamedTuple, b::HouseholdBlock, ss_end = nothing) where {TF}
-    xv, xp = unpack(xVec_endog)
+function BackwardIteration(xVec_endog::AbstractVector{TF}, exog_paths::NamedTuple, model::SequenceModel, ss_end) where {TF<:HankReal}
+    _is_ks(model) || return invoke(BackwardIteration, Tuple{Any,NamedTuple,SequenceModel,Any}, xVec_endog, exog_paths, model, ss_end)
+    b = _block(model)
+    _set_terminal!(b, ss_end)
+    xv, xp = _unpack(xVec_endog)
     K = size(xp, 2)
-    X = reshape(xv, 4, b.P)
-    r = X[3, :]; w = X[4, :]
+    X = reshape(xv, b.n_endog, b.P)
+    r = X[b.ir, :]; w = X[b.iw, :]
     dr = Matrix{Float64}(undef, b.P, K); dw = similar(dr)
     for k in 1:K
-        D = reshape(view(xp, :, k), 4, b.P)
-        dr[:, k] .= D[3, :]; dw[:, k] .= D[4, :]
+        D = reshape(view(xp, :, k), b.n_endog, b.P)
+        dr[:, k] .= D[b.ir, :]; dw[:, k] .= D[b.iw, :]
     end
-    check(b, ccall((:hank_backward, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}),
-                   b.ctx, r, w, K, dr, dw))
+    check(b.ctx, ccall((:hank_backward, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}),
+                       b.ctx, r, w, K, dr, dw))
+    b.K = K
     (KD = DevicePolicies{TF}(b, K),)
 end
 
 """
-    ForwardIteration(policy_seqs, blk, ss_initial) -> (KD = Vector,)
+    ForwardIteration(policy_seqs::NamedTuple, model::SequenceModel, ss_initial)
 
-ForwardIteration.jl:253-311 on the device-resident policies left by `BackwardIteration`.
+ForwardIteration.jl:253-311 on the device-resident policies left by `BackwardIteration` (`hank_forward`).
+Host policy matrices (any other `policy_seqs`) go to the reference's method, or to `hank_forward_policies`
+through `ForwardIterationDevice` below.
 """
-function ForwardIteration(policy_seqs::NamedTuple{(:KD,),Tuple{DevicePolicies{TF}}}, b::HouseholdBlock, ss_initial = nothing) where {TF}
+function ForwardIteration(policy_seqs::NamedTuple{(:KD,),<:Tuple{DevicePolicies{TF}}}, model::SequenceModel, ss_initial) where {TF}
+    b = policy_seqs.KD.blk
+    _set_initial!(b, model, ss_initial)
     K = policy_seqs.KD.K
     KD = Vector{Float64}(undef, b.P); dKD = Matrix{Float64}(undef, b.P, K)
-    check(b, ccall((:hank_forward, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), b.ctx, KD, dKD))
-    (KD = repack(TF, KD, dKD),)
+    check(b.ctx, ccall((:hank_forward, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), b.ctx, KD, dKD))
+    (KD = _repack(TF, KD, dKD),)
 end
 
-"""fullFunction(x) of NewtonRaphson.jl:77-83 on the device (sweeps + residuals); keeps the linearisation."""
-function fullFunction(b::HouseholdBlock, x::Vector{Float64}, Z::Vector{Float64})
-    F = Vector{Float64}(undef, length(x))
-    check(b, ccall((:hank_ks_linearize, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), b.ctx, x, Z, F))
-    F
-end
-
-"""
-    JVP(blk, primal, tangent[s]; Z) -> SparseVector / Matrix
-
-`JVP(func, primal, tangent)` of GeneralStructures.jl:542-550 for `func = fullFunction`; a matrix of
-tangents (n x K) rides as K lanes in one pass — the batched entry ForwardDiff's chunking (<= 12
-lanes, prelude.jl:1-11) cannot express.
-"""
-function JVP(b::HouseholdBlock, primal::Vector{Float64}, tangents::AbstractVecOrMat{Float64}; Z::Vector{Float64})
-    fullFunction(b, primal, Z)
-    V = tangents isa AbstractVector ? reshape(Vector{Float64}(tangents), :, 1) : Matrix{Float64}(tangents)
-    JV = similar(V)
-    check(b, ccall((:hank_ks_jvp, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}), b.ctx, size(V, 2), V, JV))
-    tangents isa AbstractVector ? sparse(vec(JV)) : JV
-end
-
-"""`(F(x), J(x)·V)` in one call (hank_ks_fjvp): the seed upload overlaps the primal backward sweep."""
-function fjvp(b::HouseholdBlock, x::Vector{Float64}, Z::Vector{Float64}, V::Matrix{Float64})
-    F = Vector{Float64}(undef, length(x)); JV = similar(V)
-    check(b, ccall((:hank_ks_fjvp, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-                   b.ctx, x, Z, size(V, 2), V, F, JV))
-    (F, JV)
-end
-
-"""Columns `cols` (a range) of the sequence-space Jacobian at `x`: directJVPJacobian (SteadyState.jl:296-320)
-generalised to any column range; the Y / KS columns skip the household sweeps."""
-function jacobian(b::HouseholdBlock, x::Vector{Float64}, Z::Vector{Float64}, cols::UnitRange{Int} = 1:length(x))
-    fullFunction(b, x, Z)
-    J = Matrix{Float64}(undef, length(x), length(cols))
-    check(b, ccall((:hank_ks_jacobian_columns, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}), b.ctx, first(cols), last(cols) + 1, J))
-    J
+"""ForwardIteration for caller-supplied `Vector{Matrix{Float64}}` policies (hank_forward_policies)."""
+function ForwardIterationDevice(policies::AbstractVector{<:AbstractMatrix{Float64}}, model::SequenceModel, ss_initial)
+    b = _block(model); _set_initial!(b, model, ss_initial)
+    pol = reduce(hcat, vec.(policies))                                   # G x P
+    KD = Vector{Float64}(undef, b.P)
+    check(b.ctx, ccall((:hank_forward_policies, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                       b.ctx, pol, 0, C_NULL, KD, C_NULL))
+    (KD = KD,)
 end
 
 """
-    NewtonRaphsonHANK(x_0, J̅, exog_paths, blk; ε = 1e-9, solver = :lu)
+    JVP(func, primal, tangents::AbstractMatrix) -> Matrix
 
-NewtonRaphson.jl:27-114 on the device.  `solver = :gmres` reproduces the reference's restarted
-GMRES(20) preconditioner solve; `:lu` factorises J̅ once; `:lu_batched` additionally assembles J(x)
-once per outer iteration from batched lanes.
+Batched companion of `JVP(func, primal, tangent)` (GeneralStructures.jl:542-550): the K columns of `tangents` ride as
+K lanes of ONE pass (`Dual{Tag,Float64,K}` seeds built like derivative.jl:12-15 builds its single one).
 """
-function NewtonRaphsonHANK(x_0::Vector{Float64}, J̅::AbstractMatrix, exog_paths::NamedTuple, b::HouseholdBlock;
-                           ε = 1e-9, solver::Symbol = :lu)
+function JVP(func::Function, primal::AbstractVector{Float64}, tangents::AbstractMatrix{Float64})
+    K = size(tangents, 2)
+    Tg = typeof(ForwardDiff.Tag(func, Float64))
+    x = [ForwardDiff.Dual{Tg}(primal[i], ForwardDiff.Partials(ntuple(k -> tangents[i, k], K))) for i in eachindex(primal)]
+    y = func(x)
+    [ForwardDiff.partials(y[i], k) for i in eachindex(y), k in 1:K]
+end
+
+"""
+    NewtonRaphsonHANK(x_0, J̅::SparseMatrixCSC, exog_paths, mod, ss_initial::SteadyState, ss_ending::SteadyState; ε = 1e-9)
+
+NewtonRaphson.jl:27-114 with the sweeps, residuals, JVPs and the preconditioner solve on the device
+(`hank_newton_solve`): same six positional arguments, same `ε`, same printed progress line per outer iteration count.
+`HankB200.NEWTON_SOLVER[]` selects the inner solve (default `:gmres`, the reference's).
+"""
+function NewtonRaphsonHANK(x_0::Vector{Float64}, J̅::SparseMatrixCSC, exog_paths::NamedTuple, mod::SequenceModel,
+                           ss_initial::SteadyState, ss_ending::SteadyState; ε = 1e-9)
+    _is_ks(mod) || return invoke(NewtonRaphsonHANK, Tuple{Vector{Float64},SparseMatrixCSC,NamedTuple,SequenceModel,Any,Any},
+                                 x_0, J̅, exog_paths, mod, ss_initial, ss_ending; ε = ε)
+    b = _block(mod)
+    _set_terminal!(b, ss_ending); _set_initial!(b, mod, ss_initial)
     n = length(x_0)
     x = Vector{Float64}(undef, n); stats = zeros(8); inner = zeros(Cint, 100)
-    code = Dict(:gmres => 0, :lu => 1, :lu_batched => 2)[solver]
-    check(b, ccall((:hank_newton_solve, LIB), Cint,
-                   (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
-                   b.ctx, Matrix{Float64}(J̅), x_0, Vector{Float64}(exog_paths.Z), ε, 1e-9, code, x, stats, inner))
-    println("Newton: $(Int(stats[1])) outer iterations, $(Int(stats[2])) JVPs, ‖y‖ = $(stats[4])")
+    code = Dict(:gmres => 0, :lu => 1, :lu_batched => 2)[HankB200.NEWTON_SOLVER[]]
+    check(b.ctx, ccall((:hank_newton_solve, LIB), Cint,
+                       (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
+                       b.ctx, Matrix{Float64}(J̅), x_0, Vector{Float64}(exog_paths.Z), ε, 1e-9, code, x, stats, inner))
+    println("Iteration: $(Int(stats[1]) + 1), norm(y): $(stats[4])   [device: $(Int(stats[2])) JVPs, inner $(Int.(inner[1:Int(stats[1])]))]")
     x
 end
 
-"""value_fn plug-in: one EGM step on the device (KrusellSmith.jl:43-83), Float64 or Dual value_next."""
-function ValueFunction(value_next::AbstractMatrix{TV}, xVals::AbstractVector{TX}, b::HouseholdBlock) where {TV,TX}
+"""
+    ValueFunction(value_next, xVals, model::SequenceModel)
+
+The `value_fn` plug-in (KrusellSmith.jl:43-83) as one device EGM step (`hank_egm_step`) for `Float64` or `Dual`
+inputs; `r` and `w` are read from `xVals` by name, as the reference does.
+"""
+function ValueFunction(value_next::AbstractMatrix{TV}, xVals::AbstractVector{TX}, model::SequenceModel) where {TV<:HankReal,TX<:HankReal}
+    HankB200.ENABLED[] || return invoke(ValueFunction, Tuple{Any,Any,SequenceModel}, value_next, xVals, model)
+    b = _block(model)
     TF = promote_type(TV, TX)
-    vv, vp = unpack(vec(value_next)); xv, xp = unpack(collect(xVals))
+    names = var_names(model); jr = findfirst(==(:r), names); jw = findfirst(==(:w), names)
+    vv, vp = _unpack(vec(value_next)); xv, xp = _unpack(collect(xVals))
     K = max(size(vp, 2), size(xp, 2))
     G = b.n_a * b.n_e
     dv = size(vp, 2) == K ? vp : zeros(G, K)
-    dr = size(xp, 2) == K ? xp[3, :] : zeros(K); dw = size(xp, 2) == K ? xp[4, :] : zeros(K)
+    dr = size(xp, 2) == K ? xp[jr, :] : zeros(K); dw = size(xp, 2) == K ? xp[jw, :] : zeros(K)
     val = Vector{Float64}(undef, G); pol = similar(val); dval = Matrix{Float64}(undef, G, K); dpol = similar(dval)
-    check(b, ccall((:hank_egm_step, LIB), Cint,
-                   (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Cint, Ptr{Float64}, Ptr{Float64},
-                    Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-                   b.ctx, vv, K == 0 ? C_NULL : dv, xv[3], xv[4], K, dr, dw, val, pol, dval, dpol))
-    sh(v, d) = reshape(repack(TF, v, d), b.n_a, b.n_e)
+    check(b.ctx, ccall((:hank_egm_step, LIB), Cint,
+                       (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Cint, Ptr{Float64}, Ptr{Float64},
+                        Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                       b.ctx, vv, K == 0 ? C_NULL : dv, xv[jr], xv[jw], K, dr, dw, val, pol, dval, dpol))
+    sh(v, d) = reshape(_repack(TF, v, d), b.n_a, b.n_e)
     (Value = sh(val, dval), KD = sh(pol, dpol))
 end
 
-end # module
+"""
+    get_xVals(asm::SSAssembler, p_vec)
+
+SteadyState.jl:111-154 with the inner VFI loop (:132-141, ~470 EGM steps per evaluation) run on the device by
+`hank_vfi` (value_fn iterated from `ones` until `max|ΔValue| < ε`, carrying the `Dual` lanes of `p_vec`); the
+stationary distribution and the aggregation stay the reference's Julia code (`make_endogenous_transition`,
+`invariant_dist`, `dot`).
+"""
+function get_xVals(asm::SSAssembler, p_vec::AbstractVector{T_num}) where {T_num<:HankReal}
+    model = asm.model
+    _is_ks(model) || return invoke(get_xVals, Tuple{SSAssembler,AbstractVector}, asm, p_vec)
+    all_keys, free_keys, endog_dim, n_exog = asm.all_keys, asm.free_keys, asm.endog_dim, asm.n_exog
+    xVals = zeros(T_num, model.compspec.n_v)
+    for (i, k) in enumerate(free_keys)
+        xVals[findfirst(==(k), all_keys)] = p_vec[i]
+    end
+    for (sym, val) in pairs(asm.ss_spec.fixed)
+        xVals[findfirst(==(sym), all_keys)] = val
+    end
+    b = _block(model)
+    jr = findfirst(==(:r), all_keys); jw = findfirst(==(:w), all_keys)
+    xv, xp = _unpack(xVals); K = size(xp, 2); G = b.n_a * b.n_e
+    val = Vector{Float64}(undef, G); pol = similar(val); dval = Matrix{Float64}(undef, G, K); dpol = similar(dval)
+    iters = Ref{Cint}(0)
+    check(b.ctx, ccall((:hank_vfi, LIB), Cint,
+                       (Ptr{Cvoid}, Float64, Float64, Cint, Ptr{Float64}, Ptr{Float64}, Float64, Cint,
+                        Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Cint}),
+                       b.ctx, xv[jr], xv[jw], K, xp[jr, :], xp[jw, :], model.compspec.ε, 10_000, val, pol, dval, dpol, iters))
+    b.terminal_id = 0   # hank_vfi uses the context's sweep buffers: the next sweep re-uploads its terminal value
+    Value = reshape(_repack(T_num, val, dval), b.n_a, n_exog)
+    KD = reshape(_repack(T_num, pol, dpol), b.n_a, n_exog)
+    Λ_endog = make_endogenous_transition(KD, endog_dim, n_exog)
+    D = invariant_dist((asm.Λ_exog * Λ_endog)')
+    xVals[findfirst(==(:KD), all_keys)] = dot(vec(KD), D)
+    return xVals, Value
+end
+
+"""Columns `cols` of the sequence-space Jacobian at `x` as unit-seed JVPs in batched lanes: `directJVPJacobian`
+(SteadyState.jl:296-320) generalised to any column range (BASELINE config 3).  Y / KS columns skip the sweeps."""
+function directJVPJacobian(x::Vector{Float64}, exog_paths::NamedTuple, model::SequenceModel, ss_initial::SteadyState,
+                           ss_ending::SteadyState, cols::UnitRange{Int})
+    b = _block(model); _set_terminal!(b, ss_ending); _set_initial!(b, model, ss_initial)
+    F = Vector{Float64}(undef, length(x))
+    check(b.ctx, ccall((:hank_ks_linearize, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                       b.ctx, x, Vector{Float64}(exog_paths.Z), F))
+    J = Matrix{Float64}(undef, length(x), length(cols))
+    check(b.ctx, ccall((:hank_ks_jacobian_columns, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}),
+                       b.ctx, first(cols), last(cols) + 1, J))
+    sparse(J)
+end
+
+# ── multi-GPU: one Julia process per GPU (Distributed / MPI.jl); the unique id travels through the host program ──
+comm_unique_id() = (id = zeros(UInt8, 128); ccall((:hank_comm_unique_id, LIB), Cint, (Ptr{UInt8},), id) == 0 || error("ncclGetUniqueId failed"); id)
+comm_init(model::SequenceModel, nranks, rank, id::Vector{UInt8}) =
+    (b = _block(model); check(b.ctx, ccall((:hank_comm_init, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), b.ctx, nranks, rank, id)))
+"""All-gather equal-sized column blocks held in host matrices (`hank_allgather_columns`): every rank passes its
+`n x k` block and receives `n x (nranks*k)`."""
+function allgather_columns(model::SequenceModel, loc::Matrix{Float64}, nranks::Int)
+    b = _block(model)
+    all = Matrix{Float64}(undef, size(loc, 1), size(loc, 2) * nranks)
+    check(b.ctx, ccall((:hank_allgather_columns, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Csize_t, Ptr{Float64}), b.ctx, loc, length(loc), all))
+    all
+end
