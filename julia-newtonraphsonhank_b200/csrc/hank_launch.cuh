@@ -206,10 +206,12 @@ static bool rowsplit_cfg(const hank_ctx* c, int K, TangentCfg* out) {
   if (K <= max_k) { *out = one; return true; }
   if (c->rs_no_multi) return false;
   // more lanes than 8-CTA clusters fit: 500 rows -> one lane per CLUSTER OF 2 (a whole period per exchange);
-  // 1000 / 2000 rows -> 2 lanes per cluster of 4, column by column; while one wave of clusters covers the pass
+  // 1000 / 2000 rows -> 2 lanes per cluster of 4, four / two columns per exchange (what fits the ring beside the
+  // exchange buffers: a hand-shake costs ~700 cycles whatever it carries); while one wave of clusters covers the pass
   TangentCfg mid; int lm;
   if (c->lda == 512) { mid = TangentCfg{256, 1, 1, 2, ne, 0}; lm = 1; }
-  else if (c->lda >= 1024) { mid = TangentCfg{c->lda / 4, 1, 2, 4, 1, 2}; lm = 2; }
+  else if (c->lda == 1024) { mid = TangentCfg{256, 1, 2, 4, 4, 0}; lm = 2; }   // 4 columns per exchange
+  else if (c->lda == 2048) { mid = TangentCfg{512, 1, 2, 4, 2, 0}; lm = 2; }   // 2 columns per exchange
   else return false;
   if (c->rs_cap[1] < 0) cm->rs_cap[1] = Sweeps<NE>::rs_max_clusters(cm, mid.NC, mid.NT, mid.L, mid.GC);
   if ((K + lm - 1) / lm <= c->rs_cap[1]) { *out = mid; return true; }

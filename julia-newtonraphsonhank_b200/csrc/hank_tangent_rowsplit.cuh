@@ -60,11 +60,16 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Both arrivals are RELAXED: with the default release semantics ptxas puts MEMBAR.ALL.CTA + ERRBAR in front of the
+// arrive, and the arriving threads have policy-tangent stores to HBM in flight, so every hand-shake waited for a DRAM
+// write round trip (19 % of the stall samples of the 2-lane shape, profiles/r02_notes.md).  What the arrivals publish
+// is shared memory written before the preceding bar.sync (which drains the stores) or a slot whose loads have
+// already been consumed; no global data is handed over through these barriers.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -115,9 +120,9 @@ __global__ void __launch_bounds__(NT + 32, 1)
 k_backward_tangent_rs(const Consts<NE> M, const Tape tp, const unsigned char* __restrict__ tape_rs, int K, int S,
                       const int* __restrict__ thi, const double* __restrict__ dr, const double* __restrict__ dw,
                       double* __restrict__ dpol) {
-  static_assert(NE % GC == 0, "exchange groups must tile the columns");
+  static_assert(GC >= 1 && GC <= NE, "columns per exchange group");   // the last group may be shorter
   static_assert(NT % 32 == 0 && (NT & (NT - 1)) == 0, "NT must be a power of two >= 32");
-  constexpr int LDA = NC * NT, NG = NE / GC, NB = 2 * LA + 2, LOGNT = ilog2c(NT), NW = NT / 32;
+  constexpr int LDA = NC * NT, NG = (NE + GC - 1) / GC, NB = 2 * LA + 2, LOGNT = ilog2c(NT), NW = NT / 32;
   constexpr int COLB = (int)rs_bw_col_bytes<NT>(), COLD = COLB / 8;   // 52*NT bytes, a multiple of 16
   constexpr int SLOTD = GC * COLD, KBD = GC * L * NT;
   constexpr bool BR = L > 1;
@@ -152,8 +157,9 @@ k_backward_tangent_rs(const Consts<NE> M, const Tape tp, const unsigned char* __
       int t = P - 1, g = 0;
       for (int gq = 0; gq < ngroups; ++gq) {
         if (gq >= S) mbar_wait(&empty[cs.i], cs.par ^ 1);
-        mbar_expect_tx(&full[cs.i], (uint32_t)(GC * COLB));
-        bulk_g2s(ring + (size_t)cs.i * SLOTD, tape_rs + (((size_t)t * NC + rank) * NE + g * GC) * COLB, GC * COLB, &full[cs.i]);
+        const uint32_t gcols = (uint32_t)min(GC, NE - g * GC);
+        mbar_expect_tx(&full[cs.i], gcols * (uint32_t)COLB);
+        bulk_g2s(ring + (size_t)cs.i * SLOTD, tape_rs + (((size_t)t * NC + rank) * NE + g * GC) * COLB, gcols * (uint32_t)COLB, &full[cs.i]);
         cs.next(S);
         if (++g == NG) { g = 0; --t; }
       }
@@ -218,6 +224,7 @@ k_backward_tangent_rs(const Consts<NE> M, const Tape tp, const unsigned char* __
           int i0[GC];
 #pragma unroll
           for (int ce = 0; ce < GC; ++ce) {
+            if ((st - LA) * GC + ce >= NE) continue;   // short last group
             cA[ce] = sl[ce * COLD + BW_CA * NT]; cB[ce] = sl[ce * COLD + BW_CB * NT];
             E1[ce] = sl[ce * COLD + BW_E1 * NT]; vf[ce] = sl[ce * COLD + BW_VF * NT];
             i0[ce] = reinterpret_cast<const int*>(sl - tid + ce * COLD + BW_NF * NT)[tid];
@@ -225,6 +232,7 @@ k_backward_tangent_rs(const Consts<NE> M, const Tape tp, const unsigned char* __
           mbar_wait(&ready[bB.i], bB.par);
 #pragma unroll
           for (int ce = 0; ce < GC; ++ce) {
+            if ((st - LA) * GC + ce >= NE) continue;
             const int i1 = i0[ce] + 1;
             const uint32_t o0 = (uint32_t)i0[ce] >> LOGNT, o1 = (uint32_t)i1 >> LOGNT;
             const int f0 = (i0[ce] & (NT - 1)) + ce * L * NT, f1 = (i1 & (NT - 1)) + ce * L * NT;
@@ -243,6 +251,7 @@ k_backward_tangent_rs(const Consts<NE> M, const Tape tp, const unsigned char* __
 #pragma unroll
           for (int ce = 0; ce < GC; ++ce) {
             const int e = st * GC + ce;
+            if (e >= NE) continue;
             const double a1 = sl[ce * COLD + BW_A1 * NT], kr = sl[ce * COLD + BW_KR * NT];
             const double cw = -(rho_t * M.z[e]);
 #pragma unroll
@@ -258,6 +267,7 @@ k_backward_tangent_rs(const Consts<NE> M, const Tape tp, const unsigned char* __
 #pragma unroll
           for (int ce = 0; ce < GC; ++ce) {
             const int e = g * GC + ce;
+            if (e >= NE) continue;
             const double ze = M.z[e];
             double* dpc = dp_t + e * L * NT;
 #pragma unroll
@@ -353,8 +363,8 @@ __global__ void __launch_bounds__(NT + 32, 1)
 k_forward_tangent_rs(const Consts<NE> M, const unsigned char* __restrict__ tape_rs, int K, int Kp, int S,
                      const int* __restrict__ thi, const double* __restrict__ zeros, const double* __restrict__ dpol,
                      int pd_rs, double* __restrict__ dkdpart) {
-  static_assert(NE % GC == 0, "exchange groups must tile the columns");
-  constexpr int LDA = NC * NT, NG = NE / GC, NB = 2 * LA + 2, NW = NT / 32;
+  static_assert(GC >= 1 && GC <= NE, "columns per exchange group");   // the last group may be shorter
+  constexpr int LDA = NC * NT, NG = (NE + GC - 1) / GC, NB = 2 * LA + 2, NW = NT / 32;
   constexpr int COLB = (int)rs_fw_tape_col_bytes<NT>(), COLD = COLB / 8;   // 36*NT + 16 bytes, a multiple of 16
   constexpr int ST_OFF = FW_NF * NT;                                       // doubles from the column start
   constexpr int PD_OFF = GC * COLD;                                        // ṗ [GC][L][NT] follows the GC tape columns
@@ -389,15 +399,16 @@ k_forward_tangent_rs(const Consts<NE> M, const unsigned char* __restrict__ tape_
     // ---- producer warp: the group's tape columns (one piece of the row-block-major tape) and ṗ of the L lanes:
     // one more piece when the backward sweep of this pass was the row-split one (pd_rs), else GC*L pieces of the
     // caller's [t][e][Kp][LDA] array (hank_forward_policies)
-    constexpr uint32_t PDB = (uint32_t)(GC * L * NT * 8);
     Cursor cs;
     int t = 0, g = 0;
     for (int gq = 0; gq < ngroups; ++gq) {
       double* dst = ring + (size_t)cs.i * SLOTD;
+      const int gcols = min(GC, NE - g * GC);
+      const uint32_t PDB = (uint32_t)(gcols * L * NT * 8);
       if (lane == 0) {
         if (gq >= S) mbar_wait(&empty[cs.i], cs.par ^ 1);
-        mbar_expect_tx(&full[cs.i], (uint32_t)(GC * COLB) + PDB);
-        bulk_g2s(dst, tape_rs + (((size_t)t * NC + rank) * NE + g * GC) * COLB, GC * COLB, &full[cs.i]);
+        mbar_expect_tx(&full[cs.i], (uint32_t)(gcols * COLB) + PDB);
+        bulk_g2s(dst, tape_rs + (((size_t)t * NC + rank) * NE + g * GC) * COLB, (uint32_t)(gcols * COLB), &full[cs.i]);
         if (t >= pe) {   // beyond the seed horizon: zeros (the page holds kZeroBytes)
           for (uint32_t o = 0; o < PDB; o += kZeroBytes)
             bulk_g2s(dst + PD_OFF + o / 8, zeros, min(PDB - o, (uint32_t)kZeroBytes), &full[cs.i]);
@@ -407,7 +418,7 @@ k_forward_tangent_rs(const Consts<NE> M, const unsigned char* __restrict__ tape_
       }
       __syncwarp();
       if (t < pe && !pd_rs)
-        for (int i = lane; i < GC * L; i += 32) {
+        for (int i = lane; i < gcols * L; i += 32) {
           const int ce = i / L, l = i - ce * L;
           bulk_g2s(dst + PD_OFF + (size_t)i * NT, dpol + ((((size_t)t * NE + g * GC + ce) * Kp + lane0 + l) * LDA + rank * NT), NT * 8,
                    &full[cs.i]);
@@ -441,13 +452,15 @@ k_forward_tangent_rs(const Consts<NE> M, const unsigned char* __restrict__ tape_
           const double* slb = ring + (size_t)sB.i * SLOTD;
 #pragma unroll
           for (int ce = 0; ce < GC; ++ce) {
+            if ((st - LA) * GC + ce >= NE) continue;   // short last group
             const int* sst = reinterpret_cast<const int*>(slb + ce * COLD + ST_OFF) + tid + 1;
             s0[ce] = sst[0]; s1[ce] = sst[1]; s2[ce] = sst[2];
           }
           mbar_wait(&ready[bB.i], bB.par);
 #pragma unroll
           for (int ce = 0; ce < GC; ++ce)
-            gather_rs_first<L, NT, BR>(xr_l + ce * L * NT, xr_l + XYD + ce * L * NT, xr_s + (uint32_t)(ce * L * NT) * 8u,
+            if ((st - LA) * GC + ce < NE)
+              gather_rs_first<L, NT, BR>(xr_l + ce * L * NT, xr_l + XYD + ce * L * NT, xr_s + (uint32_t)(ce * L * NT) * 8u,
                                        xr_s + (uint32_t)(XYD + ce * L * NT) * 8u, s0[ce], s1[ce], s2[ce], rank, xv[ce], yv[ce]);
         };
         if (LA > 0 && st >= LA) B1();
@@ -458,6 +471,7 @@ k_forward_tangent_rs(const Consts<NE> M, const unsigned char* __restrict__ tape_
 #pragma unroll
           for (int ce = 0; ce < GC; ++ce) {
             const int e = st * GC + ce;
+            if (e >= NE) continue;
             double pd[L];
 #pragma unroll
             for (int l = 0; l < L; ++l) pd[l] = sl[PD_OFF + (ce * L + l) * NT];
@@ -487,6 +501,7 @@ k_forward_tangent_rs(const Consts<NE> M, const unsigned char* __restrict__ tape_
 #pragma unroll
           for (int ce = 0; ce < GC; ++ce) {
             const int e = g * GC + ce;
+            if (e >= NE) continue;
             double acc[L];
 #pragma unroll
             for (int l = 0; l < L; ++l) {   // 0 + x0 + y0 + x1 + y1: the order of gather_row's predicated chain
