@@ -319,13 +319,46 @@ static int copy_out(hank_ctx* c, T* dst_dense, const T* src_padded, size_t rows)
 }
 
 // Tangent pass over the current tape for lanes given by dr/dw (already on device, [K][P]).
+static int tangent_pass_range(hank_ctx* c, int P, int K, int k0, double* dpol) {
+  const size_t o = (size_t)k0 * P;
+  RC(sw_backward_tangent(c, P, K, c->d_dr + o, c->d_dw + o, nullptr, dpol, nullptr));
+  return HANK_OK;
+}
 static int tangent_pass(hank_ctx* c, int P, int K) {
-  RC(sw_backward_tangent(c, P, K, c->d_dr, c->d_dw, nullptr, c->d_dpol, nullptr));
+  // Unit-seed passes a few lanes larger than one wave of 4-lane CTAs (the 598 household lanes of the T = 300
+  // Jacobian on 148 SMs): the forward sweep has no short CTAs to pack behind the long ones, so the lanes beyond the
+  // wave would cost a second full sweep (or the slower 6-lane shape).  They go through the row-split clusters
+  // instead, which finish a handful of lanes in a third of a sweep.  The cut is at a horizon-group boundary.
+  int K1 = K;
+  if (c->pass_thi && !c->no_rowsplit && c->lda == 512 && K > 4 * c->sm_count) {
+    const int wave = 4 * c->sm_count / kThiGroup * kThiGroup;
+    (void)sw_lanes_per_cta(c, 1);   // makes sure the cluster capacity has been asked
+    if (K - wave <= std::min(c->rs_cap[0], kThiGroup * 2) && K - wave > 0) K1 = wave;
+  }
+  const int* thi = c->pass_thi;
+  const int Kp_all = c->pass_Kp;
+  double* dpol2 = c->d_dpol + (size_t)P * c->n_e * (size_t)K1 * c->lda;   // policy tangents of the lanes beyond the cut
+  if (K1 < K) c->pass_Kp = K1;
+  RC(tangent_pass_range(c, P, K1, 0, c->d_dpol));
+  if (K1 < K) {
+    c->pass_thi = thi + K1 / kThiGroup;
+    RC(tangent_pass_range(c, P, K - K1, K1, dpol2));
+    c->pass_thi = thi;
+  }
   RC(join_side(c));  // the forward tangent needs the forward tape of the linearisation
   int nw = 16;
-  RC(sw_forward_tangent(c, P, K, c->d_dpol, c->d_dkdpart, &nw));
-  k_reduce_partials<<<nblk((size_t)K * P), 256, 0, c->stream>>>(c->d_dkdpart, nw, K * P, c->d_dKD);
+  RC(sw_forward_tangent(c, P, K1, c->d_dpol, c->d_dkdpart, &nw));
+  k_reduce_partials<<<nblk((size_t)K1 * P), 256, 0, c->stream>>>(c->d_dkdpart, nw, K1 * P, c->d_dKD);
   c->launches++;
+  if (K1 < K) {
+    double* part2 = c->d_dkdpart + (size_t)K1 * P * 16;
+    c->pass_thi = thi + K1 / kThiGroup;
+    int rc = sw_forward_tangent(c, P, K - K1, dpol2, part2, &nw);
+    c->pass_thi = thi; c->pass_Kp = Kp_all;
+    RC(rc);
+    k_reduce_partials<<<nblk((size_t)(K - K1) * P), 256, 0, c->stream>>>(part2, nw, (K - K1) * P, c->d_dKD + (size_t)K1 * P);
+    c->launches++;
+  }
   return cuda_check(c, cudaGetLastError(), "k_reduce_partials");
 }
 

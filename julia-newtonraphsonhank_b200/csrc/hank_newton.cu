@@ -148,6 +148,115 @@ __global__ void k_xmy(double* x, const double* y, int n) {
   if (i < n) x[i] -= y[i];
 }
 
+// ---- the whole inner loop of y_Iteration (NewtonRaphson.jl:94-106) in ONE cooperative launch (batched mode) ---------
+// Per iteration: part = J(x)·y by column splits; rhs = F − Σ part; part = J̅⁻¹·rhs; R = Σ part, y_old = y,
+// y = y_old + α R; stop when the reference's loop test eps_inner < ||y − y_old|| fails.  Grid = row blocks x kSplit
+// column splits, three grid barriers per iteration; same column ranges and the same in-order sums as k_gemv_partial /
+// k_sub_partial / k_update_from_partial, so the iterates are the ones the kernel-per-step path produces.
+// scal: [0] ||y − y_old||, [1] ||y||, [3] iterations run (added).  npart: [rows blocks][2] norm partials.
+constexpr int kInnerRows = 128;    // rows per CTA
+constexpr int kInnerQ = 2;         // column halves of a split inside a CTA: kInnerRows x kInnerQ threads
+constexpr int kInnerBlock = kInnerRows * kInnerQ;
+// Grid barrier on a monotone 64-bit arrival counter (zeroed by the host before the launch; the cooperative launch
+// guarantees that every CTA is resident).  Data written by other CTAs is read with ld.global.cg afterwards.
+__device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned long long nblocks, unsigned long long& gen) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ++gen;
+    __threadfence();
+    atomicAdd(ctr, 1ULL);
+    const unsigned long long want = gen * nblocks;
+    unsigned long long seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(ctr) : "memory");
+    } while (seen < want);
+  }
+  __syncthreads();
+}
+// Σ_k p[k * stride] for k < kSplit, ascending k, with all loads in flight before the first add (a dependent chain of
+// L2 round trips otherwise: 16 x ~700 cycles)
+__device__ __forceinline__ double sum_partials(const double* p, size_t stride) {
+  double v[kSplit];
+#pragma unroll
+  for (int k = 0; k < kSplit; ++k) v[k] = __ldcg(p + (size_t)k * stride);
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < kSplit; ++k) s += v[k];
+  return s;
+}
+__global__ void __launch_bounds__(kInnerBlock, 2)
+k_newton_inner(const double* __restrict__ Jx, const double* __restrict__ Jinv, const double* __restrict__ F, int n,
+               double alpha, double eps_inner, int max_it, double* y, double* yold, double* R, double* part,
+               double* npart, double* scal, unsigned long long* bar_ctr) {
+  const unsigned long long nblocks = (unsigned long long)gridDim.x * gridDim.y;
+  unsigned long long gen = 0;
+  constexpr int kMaxCs = (4096 + kSplit - 1) / kSplit;
+  __shared__ double vs[kMaxCs + 8];                    // this split's slice of the multiplied vector
+  __shared__ double qs[kInnerQ][kInnerRows];           // the column quarters' partial sums
+  __shared__ double red[33];
+  const int rb = blockIdx.x, s = blockIdx.y, nrb = gridDim.x;
+  const int r = threadIdx.x % kInnerRows, q = threadIdx.x / kInnerRows;
+  const int i = rb * kInnerRows + r;
+  const int cs = (n + kSplit - 1) / kSplit, j0 = s * cs, j1 = min(n, j0 + cs);
+  const int cq = (j1 - j0 + kInnerQ - 1) / kInnerQ, q0 = j0 + q * cq, q1 = min(j1, q0 + cq);
+  // part[s][i] = Σ_{j in split} A[i + j n] vs[j - j0]: each quarter of the CTA sums its columns in ascending order with
+  // up to 20 loads in flight per thread, the quarters are added in ascending order
+  auto gemv_split = [&](const double* A) {
+    double acc = 0.0;
+    if (i < n) {
+      const double* a = A + (size_t)q0 * n + i;
+#pragma unroll 20
+      for (int j = q0; j < q1; ++j, a += n) acc = fma(__ldg(a), vs[j - j0], acc);
+    }
+    qs[q][r] = acc;
+    __syncthreads();
+    if (q == 0 && i < n) {
+      double t = qs[0][r];
+#pragma unroll
+      for (int k = 1; k < kInnerQ; ++k) t += qs[k][r];
+      part[(size_t)s * n + i] = t;
+    }
+  };
+  int it = 0;
+  for (; it < max_it; ++it) {
+    for (int j = j0 + threadIdx.x; j < j1; j += kInnerBlock) vs[j - j0] = __ldcg(y + j);
+    __syncthreads();
+    gemv_split(Jx);
+    grid_barrier(bar_ctr, nblocks, gen);
+    for (int j = j0 + threadIdx.x; j < j1; j += kInnerBlock) vs[j - j0] = F[j] - sum_partials(part + j, (size_t)n);   // rhs = F − J(x) y
+    grid_barrier(bar_ctr, nblocks, gen);                         // everyone has read the first partials
+    gemv_split(Jinv);
+    grid_barrier(bar_ctr, nblocks, gen);
+    if (s == 0) {                                                // one CTA per row block updates its rows
+      double d = 0.0, qq = 0.0;
+      if (q == 0 && i < n) {
+        const double rr = sum_partials(part + i, (size_t)n);
+        R[i] = rr;
+        const double yo = __ldcg(y + i), yn = yo + alpha * rr;
+        yold[i] = yo; y[i] = yn;
+        const double t = yn - yo;
+        d = t * t; qq = yn * yn;
+      }
+      d = block_sum(d, red);
+      qq = block_sum(qq, red);
+      if (threadIdx.x == 0) { npart[2 * rb] = d; npart[2 * rb + 1] = qq; }
+    }
+    grid_barrier(bar_ctr, nblocks, gen);
+    double d = 0.0, qq = 0.0;
+    for (int b0 = 0; b0 < nrb; b0 += 8) {                        // eight row blocks' partials in flight at a time
+      double dv[8], qv[8];
+#pragma unroll
+      for (int b = 0; b < 8; ++b) { dv[b] = b0 + b < nrb ? __ldcg(npart + 2 * (b0 + b)) : 0.0; qv[b] = b0 + b < nrb ? __ldcg(npart + 2 * (b0 + b) + 1) : 0.0; }
+#pragma unroll
+      for (int b = 0; b < 8; ++b) { d += dv[b]; qq += qv[b]; }
+    }
+    const double diff = sqrt(d);
+    if (rb == 0 && s == 0 && threadIdx.x == 0) { scal[0] = diff; scal[1] = sqrt(qq); }
+    if (!(eps_inner < diff)) { ++it; break; }                    // also leaves on a non-finite step
+  }
+  if (rb == 0 && s == 0 && threadIdx.x == 0) scal[3] += (double)it;
+}
+
 // ---- GMRES pieces (single block each; n ~ 10^3) -------------------------------------------
 // gs: [0]=beta(residual.β) [1]=accumulator [2]=current [3]=beta of the cycle (init! return)
 // V[:,0] = (b − Σ part) / β
@@ -448,7 +557,34 @@ extern "C" int hank_newton_solve(hank_ctx* c, const double* Jbar, const double* 
     RC(read_scal());
     double diff = h_scal[0];
     int inner = 0;
-    if (batched && eps_inner >= 0.0 && eps_inner < diff) {
+    bool inner_done = false;
+    if (batched && eps_inner >= 0.0 && eps_inner < diff && n <= 4096 && getenv("HANK_NEWTON_NO_COOP") == nullptr) {
+      // the whole inner loop in one cooperative launch (all CTAs resident: checked against the device's occupancy)
+      const dim3 cgrid((n + kInnerRows - 1) / kInnerRows, kSplit);
+      int per_sm = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_newton_inner, kInnerBlock, 0) == cudaSuccess &&
+          (long)per_sm * c->sm_count >= (long)cgrid.x * cgrid.y) {
+        double* npart = B.H;   // the GMRES Hessenberg block is unused in this mode: 2 doubles per row block
+        CK(cudaMemsetAsync(B.scal + 2, 0, 2 * sizeof(double), c->stream));
+        unsigned long long* a_ctr = reinterpret_cast<unsigned long long*>(B.H + 64);
+        CK(cudaMemsetAsync(a_ctr, 0, sizeof(unsigned long long), c->stream));
+        const double* a_Jx = Jx; const double* a_Ji = B.J; const double* a_F = B.Fx;
+        int a_n = n, a_max = 1 << 20; double a_alpha = 0.5, a_eps = eps_inner;
+        double *a_y = B.y, *a_yold = B.yold, *a_R = B.R, *a_part = B.part, *a_np = npart, *a_scal = B.scal;
+        void* args[] = {&a_Jx, &a_Ji, &a_F, &a_n, &a_alpha, &a_eps, &a_max, &a_y, &a_yold, &a_R, &a_part, &a_np, &a_scal, &a_ctr};
+        CK(cudaLaunchCooperativeKernel((const void*)k_newton_inner, cgrid, dim3(kInnerBlock), args, 0, c->stream));
+        c->launches++;
+        CK(cudaMemcpyAsync(h_scal, B.scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        diff = h_scal[0]; ynorm = h_scal[1];
+        inner = (int)h_scal[3]; jvps += inner;
+        if (!std::isfinite(diff)) return set_error(c, HANK_ERR_NOCONV, "Newton inner iteration diverged (non-finite step)");
+        inner_done = true;
+      } else {
+        cudaGetLastError();
+      }
+    }
+    if (!inner_done && batched && eps_inner >= 0.0 && eps_inner < diff) {
       // Speculative inner loop: iterations are queued kSpec at a time, the update kernel raises a device flag when
       // the loop test fails and everything queued behind it returns at once, so the host synchronises once per
       // kSpec iterations instead of once per iteration.  Same iterates, same count.
