@@ -407,6 +407,7 @@ int hank_ctx_create(hank_ctx** out, int device, int n_a, int n_e, int T, const d
   { const char* nt = getenv("HANK_NO_DSMEM"); c->no_dsmem = nt && nt[0] == '1'; }
   { const char* nt = getenv("HANK_NO_SKIP"); c->no_skip = nt && nt[0] == '1'; }
   { const char* nt = getenv("HANK_NO_ROWSPLIT"); c->no_rowsplit = nt && nt[0] == '1'; }
+  { const char* nt = getenv("HANK_NO_RING_NE"); c->no_ring_ne = nt && nt[0] == '1'; }
   { const char* nt = getenv("HANK_RS_MAXK"); c->rs_max_k = nt ? atoi(nt) : 0; }
   { const char* nt = getenv("HANK_RS_NO_MULTI"); c->rs_no_multi = nt && nt[0] == '1'; }
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));

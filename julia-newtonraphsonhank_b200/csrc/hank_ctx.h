@@ -69,6 +69,7 @@ struct hank_ctx {
   bool no_wide = false;          // HANK_NO_WIDE=1: never use the 256-thread / 6-lane tangent shape
   bool no_tma = false;           // HANK_NO_TMA=1: use the register-prefetch tangent kernels
   bool no_skip = false;          // HANK_NO_SKIP=1: unit-seed Jacobian lanes sweep all periods
+  bool no_ring_ne = false;       // HANK_NO_RING_NE=1: backward tangent always through the runtime-sized ring
   bool no_rowsplit = false;      // HANK_NO_ROWSPLIT=1: never split a lane group's rows over a cluster
   bool rs_no_multi = false;      // HANK_RS_NO_MULTI=1: no multi-lane row-split clusters (mid lane counts run one CTA per lane)
   int rs_max_k = 0;              // HANK_RS_MAXK: lane count up to which 1-lane row-split clusters are used (0: sm_count / NC)

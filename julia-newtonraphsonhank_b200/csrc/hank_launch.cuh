@@ -251,6 +251,14 @@ static int bt_launch(hank_ctx* c, int P, int K, const double* dr, const double* 
   const int Kp = c->pass_Kp ? c->pass_Kp : grid * L;   // lane stride of the policy tangents (>= grid * L)
   c->Kp_last = Kp; c->dpol_rs = false;
   constexpr int LDA = NT * R;
+  // one ring slot per income state (compile-time slot addresses, hank_tangent_tma.cuh) where the n_e chunks fit
+  if constexpr (bt_ring_ne_smem<NE, LDA, L>() <= 232448 && L != 6 && L != 3)
+    if (!c->no_tma && !c->no_ring_ne && dvalT == nullptr && dvf == nullptr && bt_ring_ne_smem<NE, LDA, L>() <= (size_t)c->smem_max) {
+      const size_t smem_r = bt_ring_ne_smem<NE, LDA, L>();
+      if (c->pass_thi)
+        HANK_LAUNCH(KIND_BT, (k_backward_tangent_ring_ne<NE, R, NT, L, true>), grid, NT, smem_r, M, c->tape, K, Kp, c->pass_thi, dr, dw, dpol);
+      HANK_LAUNCH(KIND_BT, (k_backward_tangent_ring_ne<NE, R, NT, L, false>), grid, NT, smem_r, M, c->tape, K, Kp, (const int*)nullptr, dr, dw, dpol);
+    }
   if constexpr (LDA <= 1024) if (!c->no_tma) {  // TMA-staged tape ring (hank_tangent_tma.cuh)
     const size_t slot = bw_chunk_bytes<LDA>();
     const size_t fixed = (size_t)2 * L * LDA * 8 + (size_t)2 * L * P * 8 + (size_t)((P + 1) & ~1) * 8 + 16 * 8 + 128;

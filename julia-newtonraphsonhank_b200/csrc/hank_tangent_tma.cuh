@@ -202,6 +202,148 @@ k_backward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int Kp, int S, 
 }
 
 // ======================================================================================
+// Backward tangent sweep with ONE RING SLOT PER INCOME STATE (S = NE).
+//
+// The kernel above spends more issue slots on ring bookkeeping than on arithmetic: of the 173 instructions a warp
+// issues per column (L = 4), 61 are FP64 and 24 memory, the other ~87 advance the slot / chunk / issuer cursors and
+// their wrap-arounds (IMAD, IADD3, VIADD, SEL, ISETP, PLOP3, R2UR; profiles/r02_notes.md).  With as many slots as
+// columns the slot of column e IS slot e: every shared-memory address of the column is a compile-time offset, the
+// barrier phase is the period's parity, the exchange buffer alternates with (e + period) & 1, and the refill of the
+// slot freed at the barrier of column e is issued by warp e from a pointer that moves once per period: 141
+// instructions per column.  The seeds of the period (ṙ, ẇ of the L lanes) are broadcast through a 2-deep shared
+// buffer that the first threads fill one period ahead, which frees the [L][P] staging arrays the seven slots need the
+// room of.
+// smem: ring[NE][bw chunk] | kb[2][L][LDA] | drw[2][2L] | full[NE].   Fits for NE * 52 * LDA + 16 L LDA <= ~225 KB
+// (500 x 7 with up to 4 lanes); other shapes keep the kernel above.  No seeded V̇ (single-step callers).
+// ======================================================================================
+template <int NE, int LDA, int L>
+constexpr size_t bt_ring_ne_smem() { return (size_t)NE * bw_chunk_bytes<LDA>() + (size_t)2 * L * LDA * 8 + (size_t)4 * L * 8 + (size_t)NE * 8 + 128; }
+
+template <int NE, int R, int NT, int L, bool SKIP>
+__global__ void __launch_bounds__(NT, 1)
+k_backward_tangent_ring_ne(const Consts<NE> M, const Tape tp, int K, int Kp, const int* __restrict__ thi,
+                           const double* __restrict__ dr, const double* __restrict__ dw, double* __restrict__ dpol) {
+  constexpr int LDA = NT * R, NW = NT / 32;
+  constexpr int CH = (int)bw_chunk_bytes<LDA>();
+  constexpr int SLOT_D = CH / 8;
+  extern __shared__ __align__(128) unsigned char smem_tma[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lane0 = blockIdx.x * L;
+  const int Pfull = M.P, P = SKIP ? min(M.P, thi[lane0 / kThiGroup]) : M.P;
+  double* ring = reinterpret_cast<double*>(smem_tma);
+  double* kbuf = ring + (size_t)NE * SLOT_D;
+  double* drw = kbuf + 2 * L * LDA;                      // [2][2L]: ṙ of the L lanes, then ẇ
+  uint64_t* full = reinterpret_cast<uint64_t*>(drw + 4 * L);
+  if (P <= 0) return;
+
+  if (tid == 0) {
+    for (int s = 0; s < NE; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  // seeds of period t for lane slot i < 2L (i < L: ṙ, else ẇ); lanes beyond K carry zeros
+  auto seed = [&](int i, int t) -> double {
+    const int l = i < L ? i : i - L;
+    if (lane0 + l >= K) return 0.0;
+    return __ldg((i < L ? dr : dw) + (size_t)(lane0 + l) * Pfull + t);
+  };
+  if (tid < 2 * L) drw[tid] = seed(tid, P - 1);
+  __syncthreads();
+  const unsigned char* bw_t = tp.bw + (size_t)(P - 1) * NE * CH;   // chunks of the current period
+  if (tid == 0)
+    for (int e = 0; e < NE; ++e) {
+      mbar_expect_tx(&full[e], CH);
+      bulk_g2s(ring + (size_t)e * SLOT_D, bw_t + (size_t)e * CH, CH, &full[e]);
+    }
+
+  double Vd[L][R][NE];
+#pragma unroll
+  for (int l = 0; l < L; ++l)
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+#pragma unroll
+      for (int e = 0; e < NE; ++e) Vd[l][j][e] = 0.0;
+
+  const size_t strideKL = (size_t)Kp * LDA;
+  double* dp_t = dpol + ((ptrdiff_t)(P - 1) * NE * Kp + lane0) * LDA + tid;
+  double* kb0 = kbuf;                 // exchange buffer of the even columns of this period
+  double* kb1 = kbuf + L * LDA;       //                     odd
+  const double* slt = ring + tid;
+  uint32_t par = 0;
+  double rho = __ldg(tp.rho + P - 1);
+  for (int t = P - 1; t >= 0; --t) {
+    const double rho_t = rho;
+    if (t > 0) rho = __ldg(tp.rho + t - 1);
+    const double* dq = drw + ((P - 1 - t) & 1) * 2 * L;
+    double drl[L], dwl[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) { drl[l] = dq[l]; dwl[l] = dq[L + l]; }
+    // next period's seeds: the other half of drw was last read a period ago (>= NE barriers back)
+    if (tid < 2 * L && t > 0) drw[(((P - 1 - t) & 1) ^ 1) * 2 * L + tid] = seed(tid, t - 1);
+    // ---- phase 0 (registers only): ĖV in place of V̇⁺
+#pragma unroll
+    for (int l = 0; l < L; ++l)
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        double ev[NE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+          double s = 0.0;
+#pragma unroll
+          for (int e2 = 0; e2 < NE; ++e2) s = fma(M.Pi[e][e2], Vd[l][j][e2], s);
+          ev[e] = s;
+        }
+#pragma unroll
+        for (int e = 0; e < NE; ++e) Vd[l][j][e] = ev[e];
+      }
+    double* dpc = dp_t;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const double* sl = slt + e * SLOT_D;
+      const int* sli = reinterpret_cast<const int*>(ring + e * SLOT_D + BW_NF * LDA) + tid;
+      double* kb = (e & 1) ? kb1 : kb0;
+      mbar_wait(&full[e], par);
+      const double cw = -(rho_t * M.z[e]);
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const double a1 = sl[BW_A1 * LDA + j * NT], kr = sl[BW_KR * LDA + j * NT];
+#pragma unroll
+        for (int l = 0; l < L; ++l)
+          kb[l * LDA + j * NT + tid] = fma(a1, Vd[l][j][e], fma(kr, drl[l], cw * dwl[l]));
+      }
+      __syncthreads();
+      // every thread is through both phases of the previous column: its slot takes the chunk that column needs next
+      // (column e-1 of period t-1; for e = 0 the last column of THIS period, six columns ahead)
+      if (warp == e % NW && lane == 0) {
+        if (e > 0) {
+          if (t > 0) { mbar_expect_tx(&full[e - 1], CH); bulk_g2s(ring + (size_t)(e - 1) * SLOT_D, bw_t - (size_t)(NE - e + 1) * CH, CH, &full[e - 1]); }
+        } else if (t < P - 1) {
+          mbar_expect_tx(&full[NE - 1], CH); bulk_g2s(ring + (size_t)(NE - 1) * SLOT_D, bw_t + (size_t)(NE - 1) * CH, CH, &full[NE - 1]);
+        }
+      }
+      const double ze = M.z[e];
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const double cA = sl[BW_CA * LDA + j * NT], cB = sl[BW_CB * LDA + j * NT];
+        const double E1 = sl[BW_E1 * LDA + j * NT], vf = sl[BW_VF * LDA + j * NT];
+        const double* kk = kb + sli[j * NT];
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+          const double pd = fma(cA, kk[l * LDA], cB * kk[l * LDA + 1]);
+          __stcs(dpc + (size_t)l * LDA + j * NT, pd);
+          Vd[l][j][e] = fma(vf, fma(ze, dwl[l], -pd), E1 * drl[l]);
+        }
+      }
+      dpc += strideKL;
+    }
+    if (NE & 1) { double* sw = kb0; kb0 = kb1; kb1 = sw; }   // an odd column count flips the buffer parity every period
+    par ^= 1;
+    bw_t -= (size_t)NE * CH;
+    dp_t -= (size_t)NE * strideKL;
+  }
+}
+
+// ======================================================================================
 // Forward tangent sweep, TMA-staged tape and ṗ stream.  Slot = forward chunk | ṗ of L lanes.
 // smem: ring[S][fw chunk + L*LDA doubles] | Xb[2][L][LDA] | Yb[2][L][LDA] | full[S]
 // A slot is only read before the column's barrier, so it is free right after it: chunk c+S is
