@@ -149,6 +149,10 @@ __device__ __forceinline__ int lower_bound_fixed(const double* __restrict__ v, i
   return pos;
 }
 
+}  // namespace hank
+#include "hank_point.cuh"
+namespace hank {
+
 // ======================================================================================
 // Backward primal sweep: EGM steps t = P..1 (BackwardIteration.jl:90-113 calling
 // KrusellSmith.jl:43-83). One CTA. Writes the policy and the tape.
@@ -192,14 +196,10 @@ k_backward_primal(const Consts<NE> M, const Tape tp, const double* __restrict__ 
           double ev = 0.0;
 #pragma unroll
           for (int e2 = 0; e2 < NE; ++e2) ev += V[j][e2] * M.Pi[e][e2];
-          const double B = M.beta * ev;
-          if (B < 0.0) raise(status, 2, a, e, t);
-          const double c = pow_c<G2>(B, M.yexp);
-          const double S = (c - w * M.z[e]) + ga;
-          ks[e * LDA + a] = rho * S;
-          // ċ = Ḃ·yexp·B^(yexp-1);  k̇ = ρ·(ċ − ẇ z) + S·ρ̇,  ρ̇ = −(ρ/(1+r))·ṙ
-          bw_fields<LDA>(tp, NE, t, e)[BW_A1 * LDA + j * NT + tid] = rho * (M.beta * (M.yexp * (G2 ? c * c * c : c / B)));
-          bw_fields<LDA>(tp, NE, t, e)[BW_KR * LDA + j * NT + tid] = -(S * (rho / opr));
+          const EulerPoint u = egm_euler_point<G2>(M, ev, w * M.z[e], ga, rho, opr, status, a, e, t);
+          ks[e * LDA + a] = u.knot;
+          bw_fields<LDA>(tp, NE, t, e)[BW_A1 * LDA + j * NT + tid] = u.a1;
+          bw_fields<LDA>(tp, NE, t, e)[BW_KR * LDA + j * NT + tid] = u.kr;
         }
       }
     }
@@ -209,41 +209,17 @@ k_backward_primal(const Consts<NE> M, const Tape tp, const double* __restrict__ 
     for (int j = 0; j < R; ++j) {
       const int a = tid + j * NT;
       if (a < n_a) {
-        const double x = g[a];
 #pragma unroll
         for (int e = 0; e < NE; ++e) {
-          const double* k = ks + e * LDA;
-          if (a > 0 && !(k[a] > k[a - 1])) raise(status, 3, a, e, t);
-          int i; double num, den; bool interior = true;
-          const double k0 = k[0], kl = k[n_a - 1];
-          if (x > kl) { i = n_a - 2; den = kl - k[i]; num = den; interior = false; }
-          else if (x < k0) { i = 0; den = k[1] - k0; num = 0.0; interior = false; }
-          else {
-            int lb = lower_bound_fixed<LDA>(k, n_a, x);  // searchsortedfirst - 1 (0-based count)
-            i = min(max(lb, 1), n_a - 1) - 1;           // find_knot_index clamp, left knot 0-based
-            num = x - k[i]; den = k[i + 1] - k[i];
-          }
-          const double delta = num / den;
-          const double gi = g[i], gi1 = g[i + 1];
-          const double q = (1.0 - delta) * gi + delta * gi1;
-          const bool cons = q < M.bc;
-          const double p = cons ? M.bc : q;
-          const double cg = (opr * x + w * M.z[e]) - p;
-          if (cg < 0.0 && !M.gamma_int) raise(status, 2, a, e, t);
-          double cgp, cgp1;
-          pow_v2<G2>(cg, M.gamma, cgp, cgp1);
-          polt[e * LDA + j * NT] = p;
-          bw_idx<LDA>(tp, NE, t, e)[j * NT + tid] = i;
-          // δ̇ = (1/den)(−k̇_i) + (−num/den²)(k̇_{i+1} − k̇_i);  q̇ = δ̇ (g_{i+1} − g_i)
-          const bool live = interior && !cons;
-          const double dg = gi1 - gi, id = 1.0 / den, nd2 = delta * id;
-          bw_fields<LDA>(tp, NE, t, e)[BW_CA * LDA + j * NT + tid] = live ? (nd2 - id) * dg : 0.0;
-          bw_fields<LDA>(tp, NE, t, e)[BW_CB * LDA + j * NT + tid] = live ? -(nd2 * dg) : 0.0;
-          // V̇ = ṙ·cg^-γ + (1+r)·(−γ)·cg^(−γ−1)·ċg,  ċg = ṙ a + ẇ z − ṗ
-          const double vf = opr * ((-M.gamma) * cgp1);
-          bw_fields<LDA>(tp, NE, t, e)[BW_VF * LDA + j * NT + tid] = vf;
-          bw_fields<LDA>(tp, NE, t, e)[BW_E1 * LDA + j * NT + tid] = cgp + vf * x;
-          V[j][e] = opr * cgp;
+          const InterpPoint q = egm_interp_point<G2, LDA>(M, ks + e * LDA, g, n_a, a, w * M.z[e], opr, status, e, t);
+          polt[e * LDA + j * NT] = q.p;
+          bw_idx<LDA>(tp, NE, t, e)[j * NT + tid] = q.i;
+          double* f = bw_fields<LDA>(tp, NE, t, e) + j * NT + tid;
+          f[BW_CA * LDA] = q.cA;
+          f[BW_CB * LDA] = q.cB;
+          f[BW_VF * LDA] = q.vf;
+          f[BW_E1 * LDA] = q.E1;
+          V[j][e] = q.vnew;
         }
       }
     }
@@ -325,22 +301,14 @@ k_forward_primal(const Consts<NE> M, const Tape tp, const double* __restrict__ g
             const int e = e0 + ee;
             if (e < NE) {
               const double p = PRE ? pc[PRE ? j : 0][PRE ? e : 0] : polt[e * LDA + j * NT];
-              const int m = lower_bound_fixed<LDA>(g, n_a, p) + 1;  // Julia searchsortedfirst, 1-based
-              double om, dco;
-              if (m == 1) { om = 1.0; dco = 0.0; }
-              else if (m > n_a) { om = 0.0; dco = 0.0; }  // all mass to node n_a via the (1-ω) leg
-              else {
-                const double dgm = g[m - 1] - g[m - 2];
-                om = (p - g[m - 2]) / dgm;
-                dco = D[j][e] / dgm;
-              }
-              X[ee * LDA + a] = om * D[j][e];
-              Y[ee * LDA + a] = (1.0 - om) * D[j][e];
-              ms[ee * LDA + a] = m;
-              fw_fields<LDA>(tp, NE, t, e)[FW_OM * LDA + j * NT + tid] = om;
-              fw_fields<LDA>(tp, NE, t, e)[FW_DCO * LDA + j * NT + tid] = dco;
+              const LotteryPoint q = lottery_point<LDA>(g, n_a, p, D[j][e]);   // m > n_a: all mass to node n_a via the (1-ω) leg
+              X[ee * LDA + a] = q.om * D[j][e];
+              Y[ee * LDA + a] = (1.0 - q.om) * D[j][e];
+              ms[ee * LDA + a] = q.m;
+              fw_fields<LDA>(tp, NE, t, e)[FW_OM * LDA + j * NT + tid] = q.om;
+              fw_fields<LDA>(tp, NE, t, e)[FW_DCO * LDA + j * NT + tid] = q.dco;
               fw_fields<LDA>(tp, NE, t, e)[FW_P * LDA + j * NT + tid] = p;
-              mbt[e * LDA + j * NT] = m;
+              mbt[e * LDA + j * NT] = q.m;
             }
           }
         }
@@ -355,12 +323,7 @@ k_forward_primal(const Consts<NE> M, const Tape tp, const double* __restrict__ g
           for (int ee = 0; ee < CS; ++ee) {
             const int e = e0 + ee;
             if (e < NE) {
-              const int hi = ms[ee * LDA + a];
-              const int lo = a == 0 ? 0 : ms[ee * LDA + a - 1];
-              if (hi < lo) raise(status, 6, a, e, t);
-              for (int row = lo + 1; row <= hi; ++row) st[ee * NS + row] = a;
-              if (a == n_a - 1)
-                for (int row = max(hi, lo) + 1; row <= n_a + 2; ++row) st[ee * NS + row] = n_a;
+              lottery_starts_point(ms + ee * LDA, st + ee * NS, n_a, a, status, e, t);
             }
           }
         }
@@ -380,10 +343,7 @@ k_forward_primal(const Consts<NE> M, const Tape tp, const double* __restrict__ g
               int* so = fw_start<LDA>(tp, NE, t, e);
               so[a + 1] = s0;
               if (a == n_a - 1) { so[a + 2] = s1; so[a + 3] = s2; }
-              double acc = 0.0;
-              for (int b = s0; b < s1; ++b) acc += X[ee * LDA + b];
-              for (int b = s1; b < s2; ++b) acc += Y[ee * LDA + b];
-              tmp[j][e] = acc;
+              tmp[j][e] = lottery_gather_point(X + ee * LDA, Y + ee * LDA, s0, s1, s2);
             }
           }
         }

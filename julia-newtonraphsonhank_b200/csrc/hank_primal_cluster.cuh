@@ -71,13 +71,10 @@ k_backward_primal_cl(const Consts<NE> M, const Tape tp, const double* __restrict
         double ev = 0.0;
 #pragma unroll
         for (int e2 = 0; e2 < NE; ++e2) ev += vrow[e2] * pi_row[e2];
-        const double B = M.beta * ev;
-        if (B < 0.0) raise(status, 2, a, e, t);
-        const double c = pow_c<G2>(B, M.yexp);
-        const double S = (c - w * ze) + g[a];
-        ks[a] = rho * S;
-        bwf[BW_A1 * LDA + j * NT] = rho * (M.beta * (M.yexp * (G2 ? c * c * c : c / B)));
-        bwf[BW_KR * LDA + j * NT] = -(S * (rho / opr));
+        const EulerPoint u = egm_euler_point<G2>(M, ev, w * ze, g[a], rho, opr, status, a, e, t);
+        ks[a] = u.knot;
+        bwf[BW_A1 * LDA + j * NT] = u.a1;
+        bwf[BW_KR * LDA + j * NT] = u.kr;
       }
     }
     __syncthreads();
@@ -87,38 +84,15 @@ k_backward_primal_cl(const Consts<NE> M, const Tape tp, const double* __restrict
     for (int j = 0; j < R; ++j) {
       const int a = tid + j * NT;
       if (a < n_a) {
-        const double x = g[a];
-        if (a > 0 && !(ks[a] > ks[a - 1])) raise(status, 3, a, e, t);
-        int i; double num, den; bool interior = true;
-        const double k0 = ks[0], kl = ks[n_a - 1];
-        if (x > kl) { i = n_a - 2; den = kl - ks[i]; num = den; interior = false; }
-        else if (x < k0) { i = 0; den = ks[1] - k0; num = 0.0; interior = false; }
-        else {
-          int lb = lower_bound_fixed<LDA>(ks, n_a, x);
-          i = min(max(lb, 1), n_a - 1) - 1;
-          num = x - ks[i]; den = ks[i + 1] - ks[i];
-        }
-        const double delta = num / den;
-        const double gi = g[i], gi1 = g[i + 1];
-        const double q = (1.0 - delta) * gi + delta * gi1;
-        const bool cons = q < M.bc;
-        const double p = cons ? M.bc : q;
-        const double cg_ = (opr * x + w * ze) - p;
-        if (cg_ < 0.0 && !M.gamma_int) raise(status, 2, a, e, t);
-        double cgp, cgp1;
-        pow_v2<G2>(cg_, M.gamma, cgp, cgp1);
-        polt[j * NT] = p;
-        bwi[j * NT] = i;
-        const bool live = interior && !cons;
-        const double dg = gi1 - gi, id = 1.0 / den, nd2 = delta * id;
-        bwf[BW_CA * LDA + j * NT] = live ? (nd2 - id) * dg : 0.0;
-        bwf[BW_CB * LDA + j * NT] = live ? -(nd2 * dg) : 0.0;
-        const double vf = opr * ((-M.gamma) * cgp1);
-        bwf[BW_VF * LDA + j * NT] = vf;
-        bwf[BW_E1 * LDA + j * NT] = cgp + vf * x;
-        const double vnew = opr * cgp;
-        vdst[a] = vnew;
-        Vlast[j] = vnew;
+        const InterpPoint q = egm_interp_point<G2, LDA>(M, ks, g, n_a, a, w * ze, opr, status, e, t);
+        polt[j * NT] = q.p;
+        bwi[j * NT] = q.i;
+        bwf[BW_CA * LDA + j * NT] = q.cA;
+        bwf[BW_CB * LDA + j * NT] = q.cB;
+        bwf[BW_VF * LDA + j * NT] = q.vf;
+        bwf[BW_E1 * LDA + j * NT] = q.E1;
+        vdst[a] = q.vnew;
+        Vlast[j] = q.vnew;
       }
     }
     cluster.sync();   // publishes this period's ∂V/∂a column; also orders the reuse of ks
@@ -187,22 +161,14 @@ k_forward_primal_cl(const Consts<NE> M, const Tape tp, const double* __restrict_
       const int a = tid + j * NT;
       if (a < n_a) {
         const double p = pc[j];
-        const int m = lower_bound_fixed<LDA>(g, n_a, p) + 1;
-        double om, dco;
-        if (m == 1) { om = 1.0; dco = 0.0; }
-        else if (m > n_a) { om = 0.0; dco = 0.0; }
-        else {
-          const double dgm = g[m - 1] - g[m - 2];
-          om = (p - g[m - 2]) / dgm;
-          dco = D[j] / dgm;
-        }
-        X[a] = om * D[j];
-        Y[a] = (1.0 - om) * D[j];
-        ms[a] = m;
-        fwf[FW_OM * LDA + j * NT] = om;
-        fwf[FW_DCO * LDA + j * NT] = dco;
+        const LotteryPoint q = lottery_point<LDA>(g, n_a, p, D[j]);
+        X[a] = q.om * D[j];
+        Y[a] = (1.0 - q.om) * D[j];
+        ms[a] = q.m;
+        fwf[FW_OM * LDA + j * NT] = q.om;
+        fwf[FW_DCO * LDA + j * NT] = q.dco;
         fwf[FW_P * LDA + j * NT] = p;
-        mbt[j * NT] = m;
+        mbt[j * NT] = q.m;
       }
     }
     __syncthreads();
@@ -211,12 +177,7 @@ k_forward_primal_cl(const Consts<NE> M, const Tape tp, const double* __restrict_
     for (int j = 0; j < R; ++j) {
       const int a = tid + j * NT;
       if (a < n_a) {
-        const int hi = ms[a];
-        const int lo = a == 0 ? 0 : ms[a - 1];
-        if (hi < lo) raise(status, 6, a, e, t);
-        for (int row = lo + 1; row <= hi; ++row) st[row] = a;
-        if (a == n_a - 1)
-          for (int row = max(hi, lo) + 1; row <= n_a + 2; ++row) st[row] = n_a;
+        lottery_starts_point(ms, st, n_a, a, status, e, t);
       }
     }
     __syncthreads();
@@ -230,9 +191,7 @@ k_forward_primal_cl(const Consts<NE> M, const Tape tp, const double* __restrict_
         const int s0 = st[a + 1], s1 = st[a + 2], s2 = st[a + 3];
         so[a + 1] = s0;
         if (a == n_a - 1) { so[a + 2] = s1; so[a + 3] = s2; }
-        double acc = 0.0;
-        for (int b = s0; b < s1; ++b) acc += X[b];
-        for (int b = s1; b < s2; ++b) acc += Y[b];
+        const double acc = lottery_gather_point(X, Y, s0, s1, s2);
         tdst[a] = acc;
       }
     }
