@@ -165,6 +165,13 @@ int hank_newton_solve(hank_ctx* ctx, const double* Jbar, const double* x0, const
                       double eps, double eps_inner, int solver, double* x_out, double* stats,
                       int* inner_counts);
 
+/* The dense contraction on its own: Ainv = A^-1 for an n x n column-major FP64 matrix (host buffers), by the
+ * hand-written blocked Gauss-Jordan inverse with partial pivoting that hank_newton_solve uses for Jbar
+ * (replaces the `gmres!(R, Jbar, rhs)` solves of NewtonRaphson.jl:97 by R = Jbar^-1 rhs, and Julia's
+ * `Jbar \ rhs` / `inv(Jbar)` for callers that want the inverse).  HANK_ERR_CUDA with a message if a pivot is
+ * exactly zero.                                                                                */
+int hank_dense_inverse(hank_ctx* ctx, int n, const double* A, double* Ainv);
+
 /* ---- multi-GPU: shard lanes, all-gather the columns ------------------------------------- */
 /* NCCL unique id (128 bytes) created on rank 0 and passed to every rank by the host program.  */
 int hank_comm_unique_id(void* id128);

@@ -19,6 +19,24 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
 
+def _deps(src, seen=None):
+    """Transitive #include "..." closure of a source (so that touching one header rebuilds only its users)."""
+    import re
+    seen = set() if seen is None else seen
+    out = []
+    try:
+        text = open(src).read()
+    except OSError:
+        return out
+    for inc in re.findall(r'^\s*#include\s+"([^"]+)"', text, flags=re.M):
+        p = os.path.normpath(os.path.join(os.path.dirname(src), inc))
+        if p not in seen and os.path.exists(p):
+            seen.add(p)
+            out.append(p)
+            out += _deps(p, seen)
+    return out
+
+
 def _newer(target, deps):
     if not os.path.exists(target):
         return True
@@ -39,14 +57,12 @@ def _compile(src, obj, log):
 def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
-    headers = glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) + \
-        [os.path.join(HERE, "..", "include", "hankb200.h")]
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     jobs, objs = [], []
     for s in srcs:
         o = os.path.join(OBJDIR, os.path.basename(s)[:-3] + ".o")
         objs.append(o)
-        if force or _newer(o, [s] + headers):
+        if force or _newer(o, [s] + _deps(s)):
             jobs.append((s, o, o[:-2] + ".log"))
     if jobs:
         with cf.ThreadPoolExecutor(max_workers=min(os.cpu_count() or 8, len(jobs))) as ex:

@@ -9,8 +9,9 @@
 //             Gram-Schmidt), R reused as the initial guess — the reference's behaviour.  The
 //             second solve `gmres!(M, J̅, Λxy)` (:98) only feeds a printed quantity (:101, :108)
 //             and is skipped.
-//   solver 1: J̅⁻¹ formed once by cuSOLVER LU (getrf/getrs on the identity), then one FP64 GEMV
-//             per inner iteration.
+//   solver 1: J̅⁻¹ formed once by the hand-written blocked Gauss-Jordan inverse of hank_dense.cu (cached across
+//             solves; HANK_CUSOLVER=1 switches back to cuSOLVER getrf/getrs on the identity for A/B runs), then
+//             one FP64 GEMV per inner iteration.
 //   solver 2: as 1, and J(x) itself is assembled once per outer iteration from batched unit-seed
 //             tangent lanes (hank_ks_jacobian_columns_dev, all SMs busy) so that the ~40 inner
 //             products J(x)·y become GEMVs instead of 40 strictly sequential single-lane sweeps.
@@ -36,6 +37,9 @@ namespace hank {
     int rc__ = (call);           \
     if (rc__) return rc__;       \
   } while (0)
+
+size_t dense_inverse_iwork(int n);                                          // hank_dense.cu
+int dense_inverse_dev(hank_ctx* c, double* X, int n, double* out, int* iw);
 
 constexpr int kSplit = 16;   // column splits of the GEMV
 constexpr int kRestartMax = 20;
@@ -449,7 +453,7 @@ extern "C" int hank_newton_solve(hank_ctx* c, const double* Jbar, const double* 
     if (c->d_newton_i) cudaFree(c->d_newton_i);
     c->d_Jinv = nullptr; c->d_newton_i = nullptr; c->jinv_bytes = 0; c->jbar_valid = false;
     CK(cudaMalloc((void**)&c->d_Jinv, need_j));
-    CK(cudaMalloc((void**)&c->d_newton_i, sizeof(int) * (n + 2)));
+    CK(cudaMalloc((void**)&c->d_newton_i, sizeof(int) * std::max<size_t>(n + 2, dense_inverse_iwork(n))));
     c->jinv_bytes = need_j;
   }
   double* Jx = nullptr;  // J(x), column-major, for the batched mode (reuses the LU scratch half)
@@ -484,8 +488,20 @@ extern "C" int hank_newton_solve(hank_ctx* c, const double* Jbar, const double* 
   CK(cudaMemcpyAsync(B.y, x0, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_Z, Z, P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemsetAsync(B.H, 0, sizeof(double) * (kRestartMax + 1) * kRestartMax, c->stream));
-  if (solver == 1 && !cached) {
-    // J̅⁻¹ once: LU (cuSOLVER getrf) then getrs on the identity
+  if (solver == 1 && !cached && getenv("HANK_CUSOLVER") == nullptr) {
+    // J̅⁻¹ once: blocked Gauss-Jordan with partial pivoting (hank_dense.cu); the second half of the buffer is the
+    // work copy, the first half becomes the inverse
+    double* W = c->d_Jinv + nn;
+    CK(cudaMemcpyAsync(W, B.J, nn * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    RC(dense_inverse_dev(c, W, n, B.J, c->d_newton_i));
+    int h_info = 0;
+    CK(cudaMemcpyAsync(&h_info, c->d_newton_i + 2 * n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (h_info > 0)
+      return set_error(c, HANK_ERR_CUDA, "LU factorisation of Jbar failed: the matrix is singular (U(" +
+                                             std::to_string(h_info) + "," + std::to_string(h_info) + ") = 0)");
+  } else if (solver == 1 && !cached) {
+    // A/B path: LU (cuSOLVER getrf) then getrs on the identity
     cusolverDnHandle_t h = (cusolverDnHandle_t)c->solver;
     if (!h) {
       if (cusolverDnCreate(&h) != CUSOLVER_STATUS_SUCCESS) return set_error(c, HANK_ERR_CUDA, "cusolverDnCreate failed");

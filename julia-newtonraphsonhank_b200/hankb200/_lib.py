@@ -54,6 +54,7 @@ SIGNATURES = {
     "hank_ks_jacobian_column_list_dev": (C.c_int, [ctx_p, C.c_int, c_ip, C.c_void_p]),
     "hank_ks_jacobian_column_list": (C.c_int, [ctx_p, C.c_int, c_ip, c_dp]),
     "hank_newton_solve": (C.c_int, [ctx_p, c_dp, c_dp, c_dp, C.c_double, C.c_double, C.c_int, c_dp, c_dp, c_ip]),
+    "hank_dense_inverse": (C.c_int, [ctx_p, C.c_int, c_dp, c_dp]),
     "hank_comm_unique_id": (C.c_int, [C.c_void_p]),
     "hank_comm_init": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_void_p]),
     "hank_allgather_columns_dev": (C.c_int, [ctx_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -263,6 +263,17 @@ class HouseholdBlock:
         return xo, dict(outer=outer, jvps=int(stats[1]), fevals=int(stats[2]), ynorm=float(stats[3]),
                         gmres_iters=int(stats[4]), inner=[int(v) for v in inner[:outer]])
 
+    def dense_inverse(self, A):
+        """A^-1 by the device's blocked Gauss-Jordan inverse (the preconditioner solve of the Newton driver)."""
+        A = np.asarray(A, dtype=np.float64)
+        n = A.shape[0]
+        if A.shape != (n, n):
+            raise ValueError("A must be square")
+        Acm = np.ascontiguousarray(A.T)
+        out = np.empty((n, n))
+        self._ck(self._L.hank_dense_inverse(self._h, n, _p(Acm), _p(out)))
+        return out.T
+
     # -- multi-GPU ------------------------------------------------------------------------------
     @staticmethod
     def comm_unique_id():

@@ -47,6 +47,19 @@ def rouwenhorst_discretization(n, rho, sigma):
     return z, Pi
 
 
+def kronecker_exogenous(processes):
+    """Several independent exogenous processes [(z_1, Pi_1), (z_2, Pi_2), ...] as ONE income dimension: the state index
+    runs over the first process fastest, e = e_1 + n_1 e_2 + ..., exactly the ordering of the reference's
+    Λ_exog = kron(Π_K', kron(…, kron(Π_1', I_{n_a}))) (ForwardIteration.jl:280-284), so Pi = kron(Pi_K, …, Pi_1) and the
+    income level of a combined state is the product of its components' levels.  The device block takes the result like
+    any other (z, Pi); state counts without a kernel instantiation are padded inside hank_ctx_create."""
+    z = np.ones(1); Pi = np.ones((1, 1))
+    for zi, Pii in processes:
+        z = np.kron(np.asarray(zi, dtype=np.float64), z)
+        Pi = np.kron(np.asarray(Pii, dtype=np.float64), Pi)
+    return z, Pi
+
+
 GRID_FUNCTIONS = {"double_exponential": double_exponential, "rouwenhorst_discretization": rouwenhorst_discretization}
 KS_EQUATIONS = ("Y=Z*KS(-1)^α", "r+δ=α*Z*KS(-1)^(α-1)", "w=(1-α)*Z*KS(-1)^α", "KS=KD")
 

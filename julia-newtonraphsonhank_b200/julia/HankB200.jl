@@ -299,6 +299,16 @@ function directJVPJacobian(x::Vector{Float64}, exog_paths::NamedTuple, model::Se
 end
 
 # ── multi-GPU: one Julia process per GPU (Distributed / MPI.jl); the unique id travels through the host program ──
+"""`inv(J̅)` on the device (`hank_dense_inverse`: the blocked Gauss-Jordan inverse `hank_newton_solve` uses for its
+preconditioner solve, NewtonRaphson.jl:97) for callers that want the inverse itself."""
+function dense_inverse(model::SequenceModel, A::AbstractMatrix{Float64})
+    b = _block(model); n = size(A, 1)
+    n == size(A, 2) || error("dense_inverse: the matrix must be square")
+    Ad = Matrix{Float64}(A); out = Matrix{Float64}(undef, n, n)
+    check(b.ctx, ccall((:hank_dense_inverse, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}), b.ctx, n, Ad, out))
+    return out
+end
+
 comm_unique_id() = (id = zeros(UInt8, 128); ccall((:hank_comm_unique_id, LIB), Cint, (Ptr{UInt8},), id) == 0 || error("ncclGetUniqueId failed"); id)
 comm_init(model::SequenceModel, nranks, rank, id::Vector{UInt8}) =
     (b = _block(model); check(b.ctx, ccall((:hank_comm_init, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), b.ctx, nranks, rank, id)))

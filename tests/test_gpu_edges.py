@@ -101,6 +101,50 @@ def test_every_compiled_income_grid(n_e):
     _compare(200, n_e, 6, 5)
 
 
+@pytest.mark.parametrize("n_e", [2, 4, 6, 8, 10])
+def test_income_grids_between_the_compiled_ones(n_e):
+    """Counts that have no kernel instantiation run on the next compiled count with absorbing zero-mass padding states
+    (hank_ctx_create): same policies, distributions and tangents as the oracle run at the true n_e, and the lottery
+    brackets of the real states bit-exact."""
+    pol_o = _compare(150, n_e, 6, 5)
+    s = synthetic(150, n_e, 6, 0)
+    blk = make_block(s["m"], 6)
+    blk.set_terminal(s["vT"]); blk.set_initial_dist(s["D0"])
+    blk.block(s["r"], s["w"])
+    m_dev = blk.brackets(3)
+    m_api, _ = blk.lottery(blk.policy(3))
+    assert m_dev.shape == (n_e, 150) and np.array_equal(m_dev, m_api)
+    D = blk.dist(6 - 1)
+    assert D.shape == (n_e, 150) and abs(D.sum() - 1.0) < 1e-12      # no mass leaks into the padding states
+    blk.close()
+
+
+def test_two_exogenous_processes_by_kronecker_product():
+    """Two independent exogenous dimensions (ForwardIteration.jl:280-284: Λ_exog = kron(Π_2', kron(Π_1', I))) are one
+    income dimension with the Kronecker transition: 2 x 3 = 6 states (run on 7), checked against the oracle."""
+    from hankb200 import model as M
+    from oracle import oracle as O
+    z1, P1 = M.rouwenhorst_discretization(3, 0.9, 0.2)
+    z2, P2 = M.rouwenhorst_discretization(2, 0.5, 0.1)
+    z, Pi = M.kronecker_exogenous([(z1, P1), (z2, P2)])
+    assert Pi.shape == (6, 6) and np.allclose(Pi.sum(axis=1), 1.0)
+    T, K, n_a = 8, 3, 120
+    m = dict(grid=O.double_exponential(n_a, 0.0, 200.0), z=z, Pi=Pi, beta=0.98, gamma=2.0, borrow_cons=0.0)
+    P = T - 1
+    vT = 1.015 * ((0.015 * m["grid"][None, :] + 1.35 * z[:, None]) + 0.1) ** (-2.0)
+    D0 = np.full((6, n_a), 1.0 / (6 * n_a))
+    t = np.arange(1, P + 1); r = 0.015 * (1 + 0.1 * 0.9 ** t); w = 1.35 * (1 + 0.05 * 0.9 ** t)
+    rng = np.random.default_rng(5); dr = rng.standard_normal((K, P)); dw = rng.standard_normal((K, P))
+    orc = make_oracle(m, T)
+    pol_o, dpol_o, _, _ = orc.backward(vT, r, w, dr, dw)
+    KD_o, dKD_o = orc.forward(D0, pol_o, dpol_o)
+    blk = make_block(m, T)
+    blk.set_terminal(vT); blk.set_initial_dist(D0)
+    KD, dKD = blk.block(r, w, dr, dw)
+    assert close(blk.policies(0), pol_o) and close(KD, KD_o) and close(dKD, dKD_o), maxerr(dKD, dKD_o)
+    blk.close()
+
+
 @pytest.mark.parametrize("gamma", [1.0, 1.5, 2.0, 3.0, 4.5])
 def test_risk_aversion_values(gamma):
     _compare(150, 7, 8, 2, gamma=gamma)
