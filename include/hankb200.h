@@ -48,7 +48,11 @@ enum hank_status {
 /* ---- context ------------------------------------------------------------------------- */
 
 /* Model constants the household block reads on every value_fn call (KrusellSmith.jl:44-52):
- * wealth grid, productivity grid z, Π, β, γ, borrow_cons, and T (GeneralStructures.jl:166-174). */
+ * wealth grid, productivity grid z, Π, β, γ, borrow_cons, and T (GeneralStructures.jl:166-174).
+ * 2 <= n_a <= 2048, 1 <= n_e <= 11.  The sweep kernels exist for n_e in {3,5,7,9,11}; any other count (an even number
+ * of income states, or the Kronecker product of several exogenous processes, ForwardIteration.jl:280-284) runs on the
+ * next of those with absorbing zero-mass padding states that never leave the device: every array of this interface
+ * keeps the caller's n_e, and the real states' results are unchanged.                            */
 int hank_ctx_create(hank_ctx** out, int device, int n_a, int n_e, int T, const double* grid,
                     const double* z, const double* Pi, double beta, double gamma,
                     double borrow_cons);

@@ -318,6 +318,27 @@ static int copy_out(hank_ctx* c, T* dst_dense, const T* src_padded, size_t rows)
                                          (size_t)c->n_a * sizeof(T), rows, cudaMemcpyDefault, c->stream), "cudaMemcpy2DAsync");
 }
 
+// Padding income states (hank_ctx_create): copies the last real column of `count` consecutive [n_e][lda] arrays into
+// their padding columns (values that keep the padding states' own recursion well-posed; they carry no mass).
+static int pad_columns(hank_ctx* c, double* arr, size_t count = 1) {
+  for (int e = c->ne_user; e < c->n_e; ++e)
+    CK(cudaMemcpy2DAsync(arr + (size_t)e * c->lda, (size_t)c->Gp * 8, arr + (size_t)(c->ne_user - 1) * c->lda, (size_t)c->Gp * 8,
+                         (size_t)c->lda * 8, count, cudaMemcpyDeviceToDevice, c->stream));
+  return HANK_OK;
+}
+// `count` consecutive caller arrays [ne_user][n_a] <-> device arrays [n_e][lda] (one 2D copy per array when padded)
+static int copy_in_grids(hank_ctx* c, double* dst, const double* src, size_t count) {
+  if (c->ne_user == c->n_e) return copy_in(c, dst, src, count * c->n_e);
+  for (size_t i = 0; i < count; ++i) RC(copy_in(c, dst + i * c->Gp, src + i * c->G, c->ne_user));
+  return HANK_OK;
+}
+template <typename T>
+static int copy_out_grids(hank_ctx* c, T* dst, const T* src, size_t count) {
+  if (c->ne_user == c->n_e) return copy_out(c, dst, src, count * c->n_e);
+  for (size_t i = 0; i < count; ++i) RC(copy_out(c, dst + i * c->G, src + i * c->Gp, c->ne_user));
+  return HANK_OK;
+}
+
 // Tangent pass over the current tape for lanes given by dr/dw (already on device, [K][P]).
 static int tangent_pass_range(hank_ctx* c, int P, int K, int k0, double* dpol) {
   const size_t o = (size_t)k0 * P;
@@ -387,17 +408,27 @@ int hank_ctx_create(hank_ctx** out, int device, int n_a, int n_e, int T, const d
   c->device = device;
   c->smem_max = (int)prop.sharedMemPerBlockOptin;
   c->sm_count = prop.multiProcessorCount;
-  c->n_a = n_a; c->n_e = n_e; c->T = T; c->P = T - 1; c->G = n_a * n_e; c->P_alloc = T - 1;
+  // The sweep kernels are instantiated for n_e in {3, 5, 7, 9, 11}.  Any other count up to 11 (an even number of income
+  // states, or the Kronecker product of two exogenous processes, ForwardIteration.jl:280-284) runs on the next
+  // instantiated count with ABSORBING, ZERO-MASS padding states appended: Pi'[pad][pad] = 1, no transitions between real
+  // and padding states, income of the last real state, terminal value of the last real state, no initial mass.  The
+  // real states' sums only gain exact zeros (x + 0*v with finite v), so their results are bit-identical to an
+  // unpadded run; the padding columns never leave the device (the caller's arrays have ne_user columns).
+  int ne_run = n_e;
+  while (ne_run < 3 || ne_run % 2 == 0) ++ne_run;
+  if (ne_run > 11) return set_error(c, HANK_ERR_ARG, "n_e must be between 1 and 11 in this build");
+  c->n_a = n_a; c->ne_user = n_e; c->n_e = ne_run; c->T = T; c->P = T - 1; c->G = n_a * n_e; c->P_alloc = T - 1;
   c->beta = beta; c->gamma = gamma; c->bc = borrow_cons;
   c->h_grid.assign(grid, grid + n_a);
   c->h_z.assign(z, z + n_e);
-  c->h_Pi.resize((size_t)n_e * n_e);
+  c->h_z.resize(ne_run, z[n_e - 1]);
+  c->h_Pi.assign((size_t)ne_run * ne_run, 0.0);
   for (int e = 0; e < n_e; ++e)
-    for (int e2 = 0; e2 < n_e; ++e2) c->h_Pi[(size_t)e * n_e + e2] = Pi[e + (size_t)n_e * e2];
+    for (int e2 = 0; e2 < n_e; ++e2) c->h_Pi[(size_t)e * ne_run + e2] = Pi[e + (size_t)n_e * e2];
+  for (int e = n_e; e < ne_run; ++e) c->h_Pi[(size_t)e * ne_run + e] = 1.0;
   for (int a = 1; a < n_a; ++a)
     if (!(grid[a] > grid[a - 1])) return set_error(c, HANK_ERR_ARG, "grid must be strictly increasing");
-  if (n_e != 3 && n_e != 5 && n_e != 7 && n_e != 9 && n_e != 11)
-    return set_error(c, HANK_ERR_ARG, "n_e must be one of 3, 5, 7, 9, 11 in this build");
+  n_e = ne_run;   // everything below sizes device storage
   Shape s;
   if (!pick_shape(n_a, &s)) return set_error(c, HANK_ERR_ARG, "n_a > 2048 is not supported in this build");
   c->lda = s.NT * s.R; c->Gp = n_e * c->lda;
@@ -526,7 +557,8 @@ int hank_reserve_lanes(hank_ctx* c, int K) {
 int hank_set_terminal(hank_ctx* c, const double* v) {
   CK(cudaSetDevice(c->device));
   RC(join_side(c));   // a side-stream forward sweep / residual of the last linearisation may still be in flight
-  RC(copy_in(c, c->d_valueT, v, c->n_e));
+  RC(copy_in(c, c->d_valueT, v, c->ne_user));
+  RC(pad_columns(c, c->d_valueT));
   CK(cudaStreamSynchronize(c->stream));
   c->have_terminal = true; c->have_backward = false; c->linearized = false;
   return HANK_OK;
@@ -534,7 +566,7 @@ int hank_set_terminal(hank_ctx* c, const double* v) {
 int hank_set_initial_dist(hank_ctx* c, const double* D0) {
   CK(cudaSetDevice(c->device));
   RC(join_side(c));   // the side-stream forward primal sweep reads d_D0
-  RC(copy_in(c, c->d_D0, D0, c->n_e));
+  RC(copy_in(c, c->d_D0, D0, c->ne_user));   // (padding columns stay zero: no mass)
   CK(cudaStreamSynchronize(c->stream));
   c->have_D0 = true; c->have_forward = false; c->linearized = false;
   return HANK_OK;
@@ -626,12 +658,20 @@ int hank_forward_policies(hank_ctx* c, const double* policy, int K, const double
   RC(join_side(c));
   const int P = c->P;
   if (K > 0) { RC(ensure_lanes(c, K)); if (K > c->Kcap) return set_error(c, HANK_ERR_ARG, "K exceeds device memory"); }
-  RC(copy_in(c, c->tape.pol, policy, (size_t)P * c->n_e));
+  RC(copy_in_grids(c, c->tape.pol, policy, (size_t)P));
+  RC(pad_columns(c, c->tape.pol, (size_t)P));   // any monotone policy does for the zero-mass padding states
   const size_t Kpf = K > 0 ? (size_t)lane_stride(c, K) : 0;
   c->Kp_last = (int)Kpf; c->dpol_rs = false;
-  for (int l = 0; l < K; ++l)  // caller [K][P][n_e][n_a] -> device [P][n_e][Kp][lda]
-    CK(cudaMemcpy2DAsync(c->d_dpol + (size_t)l * c->lda, Kpf * c->lda * 8, dpolicy + (size_t)l * P * c->G,
-                         (size_t)c->n_a * 8, (size_t)c->n_a * 8, (size_t)P * c->n_e, cudaMemcpyDefault, c->stream));
+  for (int l = 0; l < K; ++l) {  // caller [K][P][n_e][n_a] -> device [P][n_e][Kp][lda]
+    if (c->ne_user == c->n_e)
+      CK(cudaMemcpy2DAsync(c->d_dpol + (size_t)l * c->lda, Kpf * c->lda * 8, dpolicy + (size_t)l * P * c->G,
+                           (size_t)c->n_a * 8, (size_t)c->n_a * 8, (size_t)P * c->n_e, cudaMemcpyDefault, c->stream));
+    else
+      for (int e = 0; e < c->ne_user; ++e)   // one copy per income state: rows are the periods
+        CK(cudaMemcpy2DAsync(c->d_dpol + ((size_t)e * Kpf + l) * c->lda, (size_t)c->n_e * Kpf * c->lda * 8,
+                             dpolicy + (size_t)l * P * c->G + (size_t)e * c->n_a, (size_t)c->G * 8, (size_t)c->n_a * 8, (size_t)P,
+                             cudaMemcpyDefault, c->stream));
+  }
   c->have_backward = false; c->linearized = false; c->K_last = K;
   RC(forward_dev(c, c->tape.pol, K, c->d_dpol, c->d_KD, c->d_dKD));
   int rc = check_status(c);
@@ -668,25 +708,26 @@ int hank_egm_step(hank_ctx* c, const double* value_next, const double* dvalue_ne
   const int Gp = c->Gp;
   RC(ensure_egm(c, K));
   double* d_vn = c->d_dvalT + (size_t)K * Gp;
-  RC(copy_in(c, d_vn, value_next, c->n_e));
+  RC(copy_in(c, d_vn, value_next, c->ne_user));
+  RC(pad_columns(c, d_vn));
   CK(cudaMemcpyAsync(c->d_r, &r, sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_w, &w, sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));  // r, w are stack temporaries
   c->have_backward = false; c->have_forward = false; c->linearized = false; c->K_last = 0;
   RC(sw_backward_primal(c, 1, d_vn, c->d_r, c->d_w));
   if (K > 0) {
-    if (dvalue_next) RC(copy_in(c, c->d_dvalT, dvalue_next, (size_t)K * c->n_e));
+    if (dvalue_next) RC(copy_in_grids(c, c->d_dvalT, dvalue_next, (size_t)K));
     CK(cudaMemcpyAsync(c->d_dr, dr, K * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_dw, dw, K * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     RC(sw_backward_tangent(c, 1, K, c->d_dr, c->d_dw, dvalue_next ? c->d_dvalT : nullptr, c->d_dpol, c->d_dvalue_first));
   }
-  RC(copy_out(c, value, c->tape.value_first, c->n_e));
-  RC(copy_out(c, policy, c->tape.pol, c->n_e));
+  RC(copy_out(c, value, c->tape.value_first, c->ne_user));
+  RC(copy_out(c, policy, c->tape.pol, c->ne_user));
   if (K > 0) {
-    RC(copy_out(c, dvalue, c->d_dvalue_first, (size_t)K * c->n_e));
+    RC(copy_out_grids(c, dvalue, (const double*)c->d_dvalue_first, (size_t)K));
     for (int l = 0; l < K; ++l)  // device [1][n_e][K][lda] -> caller [K][n_e][n_a]
       CK(cudaMemcpy2DAsync(dpolicy + (size_t)l * c->G, (size_t)c->n_a * 8, c->d_dpol + (size_t)l * c->lda,
-                           (size_t)c->Kp_last * c->lda * 8, (size_t)c->n_a * 8, c->n_e, cudaMemcpyDefault, c->stream));
+                           (size_t)c->Kp_last * c->lda * 8, (size_t)c->n_a * 8, c->ne_user, cudaMemcpyDefault, c->stream));
   }
   return check_status(c);
 }
@@ -743,7 +784,7 @@ int hank_vfi(hank_ctx* c, double r, double w, int K, const double* dr, const dou
   RC(step());
   int it = 0;
   for (; it < max_iter; ++it) {
-    k_max_abs_diff<<<1, 1024, 0, c->stream>>>(c->tape.value_first, d_v, c->n_e, c->lda, c->n_a, d_tol);
+    k_max_abs_diff<<<1, 1024, 0, c->stream>>>(c->tape.value_first, d_v, c->ne_user, c->lda, c->n_a, d_tol);
     c->launches++;
     CK(cudaMemcpyAsync(d_v, c->tape.value_first, (size_t)Gp * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     if (K > 0) CK(cudaMemcpyAsync(c->d_dvalT, c->d_dvalue_first, (size_t)K * Gp * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
@@ -754,13 +795,13 @@ int hank_vfi(hank_ctx* c, double r, double w, int K, const double* dr, const dou
     RC(step());
   }
   if (iters) *iters = it;
-  RC(copy_out(c, value, (const double*)c->tape.value_first, c->n_e));
-  RC(copy_out(c, policy, (const double*)c->tape.pol, c->n_e));
+  RC(copy_out(c, value, (const double*)c->tape.value_first, c->ne_user));
+  RC(copy_out(c, policy, (const double*)c->tape.pol, c->ne_user));
   if (K > 0) {
-    RC(copy_out(c, dvalue, (const double*)c->d_dvalue_first, (size_t)K * c->n_e));
+    RC(copy_out_grids(c, dvalue, (const double*)c->d_dvalue_first, (size_t)K));
     for (int l = 0; l < K; ++l)
       CK(cudaMemcpy2DAsync(dpolicy + (size_t)l * c->G, (size_t)c->n_a * 8, c->d_dpol + (size_t)l * c->lda,
-                           (size_t)c->Kp_last * c->lda * 8, (size_t)c->n_a * 8, c->n_e, cudaMemcpyDefault, c->stream));
+                           (size_t)c->Kp_last * c->lda * 8, (size_t)c->n_a * 8, c->ne_user, cudaMemcpyDefault, c->stream));
   }
   return check_status(c);
 }
@@ -769,7 +810,7 @@ int hank_vfi(hank_ctx* c, double r, double w, int K, const double* dr, const dou
 int hank_get_policy(hank_ctx* c, int t, int lane, double* out) {
   CK(cudaSetDevice(c->device));
   if (t < 1 || t > c->P || lane < 0 || lane > c->K_last) return set_error(c, HANK_ERR_ARG, "t or lane out of range");
-  if (lane == 0) RC(copy_out(c, out, (const double*)(c->tape.pol + (size_t)(t - 1) * c->Gp), c->n_e));
+  if (lane == 0) RC(copy_out(c, out, (const double*)(c->tape.pol + (size_t)(t - 1) * c->Gp), c->ne_user));
   else  // tangents are [t][e][K][lda]
   {
     const size_t Kp = (size_t)c->Kp_last;
@@ -778,7 +819,7 @@ int hank_get_policy(hank_ctx* c, int t, int lane, double* out) {
       const int L = c->dpol_rs_L, NC = c->dpol_rs_NC, NT = c->lda / NC, cl = (lane - 1) / L, l = (lane - 1) % L;
       const double* base = c->d_dpol + (((size_t)(t - 1) * c->dpol_rs_ncl + cl) * NC) * ((size_t)c->n_e * L * NT);
       const size_t full = (size_t)c->n_a / NT, rem = (size_t)c->n_a % NT;
-      for (int e = 0; e < c->n_e; ++e) {
+      for (int e = 0; e < c->ne_user; ++e) {
         const double* src = base + ((size_t)e * L + l) * NT;
         if (full) CK(cudaMemcpy2DAsync(out + (size_t)e * c->n_a, (size_t)NT * 8, src, (size_t)c->n_e * L * NT * 8, (size_t)NT * 8, full,
                                        cudaMemcpyDefault, c->stream));
@@ -787,7 +828,7 @@ int hank_get_policy(hank_ctx* c, int t, int lane, double* out) {
       }
     } else
     CK(cudaMemcpy2DAsync(out, (size_t)c->n_a * 8, c->d_dpol + ((size_t)(t - 1) * c->n_e * Kp + (lane - 1)) * c->lda,
-                         Kp * c->lda * 8, (size_t)c->n_a * 8, c->n_e, cudaMemcpyDefault, c->stream));
+                         Kp * c->lda * 8, (size_t)c->n_a * 8, c->ne_user, cudaMemcpyDefault, c->stream));
   }
   CK(cudaStreamSynchronize(c->stream));
   return HANK_OK;
@@ -799,14 +840,14 @@ int hank_get_dist(hank_ctx* c, int t, double* out) {
   if (t < 1 || t > c->P) return set_error(c, HANK_ERR_ARG, "t out of range");
   // D_t sits in field FW_D of each column chunk: [t][e][FW_NF][lda]
   CK(cudaMemcpy2DAsync(out, (size_t)c->n_a * 8, c->tape.fw + (size_t)(t - 1) * c->n_e * fw_chunk(c) + (size_t)FW_D * c->lda * 8,
-                       fw_chunk(c), (size_t)c->n_a * 8, c->n_e, cudaMemcpyDefault, c->stream));
+                       fw_chunk(c), (size_t)c->n_a * 8, c->ne_user, cudaMemcpyDefault, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return HANK_OK;
 }
 int hank_get_value_first(hank_ctx* c, int lane, double* out) {
   CK(cudaSetDevice(c->device));
   if (lane != 0) return set_error(c, HANK_ERR_ARG, "only the primal value is retained by the sweeps");
-  RC(copy_out(c, out, (const double*)c->tape.value_first, c->n_e));
+  RC(copy_out(c, out, (const double*)c->tape.value_first, c->ne_user));
   CK(cudaStreamSynchronize(c->stream));
   return HANK_OK;
 }
@@ -815,7 +856,7 @@ int hank_get_brackets(hank_ctx* c, int t, int32_t* m) {
   RC(join_side(c));
   if (!c->have_forward) return set_error(c, HANK_ERR_STATE, "no forward sweep has been run");
   if (t < 1 || t > c->P) return set_error(c, HANK_ERR_ARG, "t out of range");
-  RC(copy_out(c, m, (const int32_t*)(c->tape.mbr + (size_t)(t - 1) * c->Gp), c->n_e));
+  RC(copy_out(c, m, (const int32_t*)(c->tape.mbr + (size_t)(t - 1) * c->Gp), c->ne_user));
   CK(cudaStreamSynchronize(c->stream));
   return HANK_OK;
 }

@@ -8,7 +8,8 @@
 
 struct hank_ctx {
   int device = 0;
-  int n_a = 0, n_e = 0, T = 0, P = 0, G = 0;
+  int n_a = 0, n_e = 0, T = 0, P = 0, G = 0;   // n_e: income states the kernels run with (>= ne_user, see hank_ctx_create)
+  int ne_user = 0;              // income states of the caller's arrays; G = n_a * ne_user
   int lda = 0, Gp = 0;          // padded leading dimension NT*R >= n_a and n_e*lda
   int P_alloc = 0;              // periods the tape / paths are allocated for
   double beta = 0, gamma = 0, bc = 0;

@@ -214,7 +214,10 @@ static bool rowsplit_cfg(const hank_ctx* c, int K, TangentCfg* out) {
   else if (c->lda == 2048) { mid = TangentCfg{512, 1, 2, 4, 2, 0}; lm = 2; }   // 2 columns per exchange
   else return false;
   if (c->rs_cap[1] < 0) cm->rs_cap[1] = Sweeps<NE>::rs_max_clusters(cm, mid.NC, mid.NT, mid.L, mid.GC);
-  if ((K + lm - 1) / lm <= c->rs_cap[1]) { *out = mid; return true; }
+  // (seed-horizon passes run their lanes longest first: a few clusters more than fit at once are the shortest ones and
+  // start behind the first to finish, so "one wave" may overflow by a sixth)
+  const int cap1 = c->pass_thi ? c->rs_cap[1] + c->rs_cap[1] / 6 : c->rs_cap[1];
+  if ((K + lm - 1) / lm <= cap1) { *out = mid; return true; }
   return false;
 }
 template <int NE>
@@ -225,8 +228,11 @@ static TangentCfg tangent_cfg(const hank_ctx* c, int K, bool allow_rowsplit = tr
   switch (c->lda) {
     case 256: return {256, 1, K >= 4 * sm ? 4 : (K >= 2 * sm ? 2 : 1)};
     case 512: {
-      if (K <= sm) return {512, 1, 1};
-      if (K <= 2 * sm) return {512, 1, 2};
+      // (same slack for seed-horizon passes: 300 unit-seed lanes of a 2-GPU Jacobian build are one wave of 2-lane CTAs
+      // plus two short ones, not half a wave of 4-lane CTAs)
+      const int wave = c->pass_thi ? sm + sm / 6 : sm;
+      if (K <= wave) return {512, 1, 1};
+      if (K <= 2 * wave) return {512, 1, 2};
       const double c4 = cfg_cost(K, 4, sm, 1.0), c6 = cfg_cost(K, 6, sm, 1.6);
       if (c6 < c4 && !c->no_wide) return {256, 2, 6};
       return {512, 1, 4};
