@@ -176,6 +176,20 @@ int hank_newton_solve(hank_ctx* ctx, const double* Jbar, const double* x0, const
  * exactly zero.                                                                                */
 int hank_dense_inverse(hank_ctx* ctx, int n, const double* A, double* Ainv);
 
+/* ---- the model's equilibrium equations as device bytecode ---------------------------------- */
+/* Replaces the built-in Krusell-Smith aggregate block by the model's own equations: the reference's compile_residuals
+ * (ModelParser.jl:217-259) + assemble_full_xMat (GeneralStructures.jl:329-377) + the ForwardDiff pass through both.
+ * Variables are numbered like var_names(model) (ModelParser.jl:357): n_endog endogenous, then the household
+ * aggregate KD, then n_exog exogenous.  After this call hank_ks_linearize / _jvp / _fjvp / _jacobian_columns /
+ * hank_newton_solve work on x of shape n_endog x P (variable fastest) and Z of shape P x n_exog (period fastest per
+ * variable: Z[v*P + t]); the household block still takes r = x[ir, :] and w = x[iw, :] (0-based rows) and returns KD.
+ * Equation i (one per endogenous variable) is the postfix program code[eq_off[i] .. eq_off[i+1]) computing LHS - RHS:
+ *   0 k: push consts[k]    1 v s: push variable v at period t+s (steady-state boundary values ss_start / ss_end of
+ *   length n_endog+1+n_exog outside 1..P)    2 + 3 - 4 * 5 / 6 ^ (binary)    7 neg 8 exp 9 log 10 sqrt (unary).
+ * hankb200/equations.py (Python) and julia/HankB200.jl (Julia) compile the YAML equation strings to this form.      */
+int hank_eq_configure(hank_ctx* ctx, int n_endog, int n_exog, int ir, int iw, const int* eq_off, const int* code,
+                      int n_const, const double* consts, const double* ss_start, const double* ss_end);
+
 /* ---- multi-GPU: shard lanes, all-gather the columns ------------------------------------- */
 /* NCCL unique id (128 bytes) created on rank 0 and passed to every rank by the host program.  */
 int hank_comm_unique_id(void* id128);

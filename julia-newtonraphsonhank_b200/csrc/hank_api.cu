@@ -101,12 +101,12 @@ __global__ void k_ks_residual_tangent(int P, int K, double alpha, double ssKS, c
   o[4 * t + 3] = d[4 * t + 1] - dKD[(size_t)l * P + t];
 }
 // Unit seeds for Jacobian columns: lane l perturbs r or w (v = 2, 3) at period tcol.
-__global__ void k_unit_seeds(int P, int K, const int* __restrict__ lane_col, double* dr, double* dw) {
+__global__ void k_unit_seeds(int P, int K, int ne, int ir, int iw, const int* __restrict__ lane_col, double* dr, double* dw) {
   int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= K) return;
-  const int col = lane_col[l], t = col >> 2, v = col & 3;
-  if (v == 2) dr[(size_t)l * P + t] = 1.0;
-  if (v == 3) dw[(size_t)l * P + t] = 1.0;
+  const int col = lane_col[l], t = col / ne, v = col - t * ne;
+  if (v == ir) dr[(size_t)l * P + t] = 1.0;
+  if (v == iw) dw[(size_t)l * P + t] = 1.0;
 }
 // Jacobian columns with unit seeds e_col: direct residual terms + household term −K̇D.
 __global__ void k_ks_jac_columns(int P, const int* __restrict__ col_ids, int ncols, double alpha, double ssKS,
@@ -284,7 +284,7 @@ static int ensure_V(hank_ctx* c, int K) {
   if (K <= c->Vcap) return HANK_OK;
   dfree(c->d_V); dfree(c->d_JV);
   c->Vcap = 0;
-  const size_t n = (size_t)4 * c->P;
+  const size_t n = (size_t)c->n_endog * c->P;
   RC(dalloc(c, &c->d_V, n * K));
   RC(dalloc(c, &c->d_JV, n * K));
   c->Vcap = K;
@@ -490,6 +490,7 @@ void hank_ctx_destroy(hank_ctx* c) {
   if (c->ev_fp) cudaEventDestroy(c->ev_fp);
   hank_comm_destroy(c);
   newton_release(c);
+  eq_release(c);
   Tape& tp = c->tape;
   dfree(c->d_grid); dfree(c->d_valueT); dfree(c->d_D0); dfree(c->d_Pi); dfree(c->d_scatter); dfree(c->d_r); dfree(c->d_w);
   dfree(tp.pol); dfree(tp.bw); dfree(tp.rho); dfree(tp.fw); dfree(tp.mbr);
@@ -882,6 +883,7 @@ int hank_lottery(hank_ctx* c, const double* policy, int32_t* m, double* omega) {
 
 // ---- Krusell-Smith F and JVPs ---------------------------------------------------------------
 int hank_ks_configure(hank_ctx* c, double alpha, double delta, double ss_start_KS) {
+  if (c->eq_on) return set_error(c, HANK_ERR_STATE, "the equations of this context were set by hank_eq_configure");
   c->alpha = alpha; c->delta = delta; c->ssKS = ss_start_KS; c->ks_ready = true; c->linearized = false;
   return HANK_OK;
 }
@@ -890,13 +892,13 @@ int hank_ks_linearize_dev(hank_ctx* c, const double* x, const double* Z, double*
   CK(cudaSetDevice(c->device));
   if (!c->ks_ready) return set_error(c, HANK_ERR_STATE, "hank_ks_configure has not been called");
   if (!c->have_terminal || !c->have_D0) return set_error(c, HANK_ERR_STATE, "terminal value / initial distribution not set");
-  const int P = c->P; const size_t n = (size_t)4 * P;
+  const int P = c->P; const size_t n = (size_t)c->n_endog * P;
   // the previous linearisation's forward sweep and residuals (side stream) read d_x, d_Z and d_KD
   RC(join_side(c));
   if (x != c->d_x) CK(cudaMemcpyAsync(c->d_x, x, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-  if (Z != c->d_Z) CK(cudaMemcpyAsync(c->d_Z, Z, P * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-  k_extract_rw<<<nblk(P), 256, 0, c->stream>>>(c->d_x, P, c->d_r, c->d_w);
-  c->launches++;
+  if (Z != c->d_Z) CK(cudaMemcpyAsync(c->d_Z, Z, (size_t)c->n_exog * P * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  if (c->eq_on) RC(eq_extract_rw(c, c->d_x, c->d_r, c->d_w));
+  else { k_extract_rw<<<nblk(P), 256, 0, c->stream>>>(c->d_x, P, c->d_r, c->d_w); c->launches++; }
   RC(backward_dev(c, c->d_r, c->d_w, 0, nullptr, nullptr));
   // The forward primal sweep and the residuals only feed the forward tangent / F: they go to the
   // high-priority side stream so that a following backward tangent sweep overlaps them.
@@ -908,9 +910,12 @@ int hank_ks_linearize_dev(hank_ctx* c, const double* x, const double* Z, double*
   }
   int rc = forward_dev(c, c->tape.pol, 0, nullptr, c->d_KD, nullptr);
   if (rc == HANK_OK) {
-    k_ks_residual<<<nblk(P), 256, 0, c->stream>>>(P, c->alpha, c->delta, c->ssKS, c->d_x, c->d_KD, c->d_Z, F);
-    c->launches++;
-    rc = cuda_check(c, cudaGetLastError(), "k_ks_residual");
+    if (c->eq_on) rc = eq_residual(c, c->d_x, c->d_KD, c->d_Z, F);
+    else {
+      k_ks_residual<<<nblk(P), 256, 0, c->stream>>>(P, c->alpha, c->delta, c->ssKS, c->d_x, c->d_KD, c->d_Z, F);
+      c->launches++;
+      rc = cuda_check(c, cudaGetLastError(), "k_ks_residual");
+    }
   }
   if (!c->no_overlap) {
     c->stream = main_stream;
@@ -925,29 +930,32 @@ int hank_ks_jvp_dev(hank_ctx* c, int K, const double* V, double* JV) {
   CK(cudaSetDevice(c->device));
   if (!c->linearized) return set_error(c, HANK_ERR_STATE, "hank_ks_jvp needs a preceding hank_ks_linearize");
   if (K < 1) return set_error(c, HANK_ERR_ARG, "K must be >= 1");
-  const int P = c->P; const size_t n = (size_t)4 * P;
+  const int P = c->P; const size_t n = (size_t)c->n_endog * P;
   RC(ensure_lanes(c, K));
   for (int k0 = 0; k0 < K; k0 += c->Kcap) {
     const int kc = std::min(c->Kcap, K - k0);
     const double* Vc = V + (size_t)k0 * n;
-    k_extract_drdw<<<nblk((size_t)kc * P), 256, 0, c->stream>>>(Vc, P, kc, c->d_dr, c->d_dw);
-    c->launches++;
+    if (c->eq_on) RC(eq_extract_drdw(c, kc, Vc, c->d_dr, c->d_dw));
+    else { k_extract_drdw<<<nblk((size_t)kc * P), 256, 0, c->stream>>>(Vc, P, kc, c->d_dr, c->d_dw); c->launches++; }
     RC(tangent_pass(c, P, kc));
     c->K_last = kc;
-    k_ks_residual_tangent<<<nblk((size_t)kc * P), 256, 0, c->stream>>>(P, kc, c->alpha, c->ssKS, c->d_x, c->d_Z, Vc,
-                                                                      c->d_dKD, JV + (size_t)k0 * n);
-    c->launches++;
-    CK(cudaGetLastError());
+    if (c->eq_on) RC(eq_residual_tangent(c, kc, c->d_x, c->d_KD, c->d_Z, Vc, nullptr, c->d_dKD, nullptr, JV + (size_t)k0 * n));
+    else {
+      k_ks_residual_tangent<<<nblk((size_t)kc * P), 256, 0, c->stream>>>(P, kc, c->alpha, c->ssKS, c->d_x, c->d_Z, Vc,
+                                                                        c->d_dKD, JV + (size_t)k0 * n);
+      c->launches++;
+      CK(cudaGetLastError());
+    }
   }
   return HANK_OK;
 }
 
 int hank_ks_linearize(hank_ctx* c, const double* x, const double* Z, double* F) {
   CK(cudaSetDevice(c->device));
-  const int P = c->P; const size_t n = (size_t)4 * P;
+  const int P = c->P; const size_t n = (size_t)c->n_endog * P;
   RC(join_side(c));   // before d_x / d_Z are overwritten
   CK(cudaMemcpyAsync(c->d_x, x, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_Z, Z, P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_Z, Z, (size_t)c->n_exog * P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   RC(hank_ks_linearize_dev(c, c->d_x, c->d_Z, c->d_F));
   RC(join_side(c));
   if (F) CK(cudaMemcpyAsync(F, c->d_F, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -959,7 +967,7 @@ int hank_ks_linearize(hank_ctx* c, const double* x, const double* Z, double* F) 
 int hank_ks_jvp(hank_ctx* c, int K, const double* V, double* JV) {
   CK(cudaSetDevice(c->device));
   if (K < 1) return set_error(c, HANK_ERR_ARG, "K must be >= 1");
-  const size_t n = (size_t)4 * c->P;
+  const size_t n = (size_t)c->n_endog * c->P;
   RC(ensure_V(c, K));
   CK(cudaMemcpyAsync(c->d_V, V, n * K * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   RC(hank_ks_jvp_dev(c, K, c->d_V, c->d_JV));
@@ -972,7 +980,7 @@ int hank_ks_jvp(hank_ctx* c, int K, const double* V, double* JV) {
 int hank_ks_fjvp(hank_ctx* c, const double* x, const double* Z, int K, const double* V, double* F, double* JV) {
   CK(cudaSetDevice(c->device));
   if (K < 1) return set_error(c, HANK_ERR_ARG, "K must be >= 1");
-  const int P = c->P; const size_t n = (size_t)4 * P;
+  const int P = c->P; const size_t n = (size_t)c->n_endog * P;
   RC(ensure_V(c, K));
   RC(ensure_lanes(c, K));
   RC(join_side(c));
@@ -980,7 +988,7 @@ int hank_ks_fjvp(hank_ctx* c, const double* x, const double* Z, int K, const dou
   CK(cudaMemcpyAsync(c->d_V, V, n * K * sizeof(double), cudaMemcpyHostToDevice, c->stream3));
   CK(cudaEventRecord(c->ev_v, c->stream3));
   CK(cudaMemcpyAsync(c->d_x, x, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_Z, Z, P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_Z, Z, (size_t)c->n_exog * P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   RC(hank_ks_linearize_dev(c, c->d_x, c->d_Z, c->d_F));
   CK(cudaStreamWaitEvent(c->stream, c->ev_v, 0));
   // A multi-wave pass is cut at CTA-wave boundaries (the first wave leaves n_e SMs to the overlapped forward
@@ -1014,11 +1022,11 @@ int hank_ks_fjvp(hank_ctx* c, const double* x, const double* Z, int K, const dou
 
 // Jacobian columns `cols` (0-based, ascending) at the linearisation point, written to J in that order.
 static int jacobian_cols_impl(hank_ctx* c, const std::vector<int>& cols, double* J) {
-  const int P = c->P, n = 4 * P;
+  const int P = c->P, ne = c->n_endog, n = ne * P;
   const int ncols = (int)cols.size();
   std::vector<int> lane_col, lane_pos, col_lane(ncols, -1), chunk_cols, thi;
   for (int j = 0; j < ncols; ++j)
-    if ((cols[j] & 3) >= 2) { lane_col.push_back(cols[j]); lane_pos.push_back(j); }
+    if (cols[j] % ne == c->eq_ir || cols[j] % ne == c->eq_iw) { lane_col.push_back(cols[j]); lane_pos.push_back(j); }
   int Kh = (int)lane_col.size();
   if (Kh > 0) RC(ensure_lanes(c, Kh));
   if (c->jac_idx_cap < ncols) {
@@ -1049,12 +1057,12 @@ static int jacobian_cols_impl(hank_ctx* c, const std::vector<int>& cols, double*
       CK(cudaMemcpyAsync(d_lane_col, chunk_cols.data(), kc * sizeof(int), cudaMemcpyHostToDevice, c->stream));
       CK(cudaMemsetAsync(c->d_dr, 0, (size_t)kc * P * sizeof(double), c->stream));
       CK(cudaMemsetAsync(c->d_dw, 0, (size_t)kc * P * sizeof(double), c->stream));
-      k_unit_seeds<<<nblk(kc), 256, 0, c->stream>>>(P, kc, d_lane_col, c->d_dr, c->d_dw);
+      k_unit_seeds<<<nblk(kc), 256, 0, c->stream>>>(P, kc, ne, c->eq_ir, c->eq_iw, d_lane_col, c->d_dr, c->d_dw);
       c->launches++;
       const int ngroups = (kc + kThiGroup - 1) / kThiGroup + 1;   // + one group of padding lanes
       if (!c->no_skip) {
         thi.assign(ngroups, 0);
-        for (int l = 0; l < kc; ++l) thi[l / kThiGroup] = std::max(thi[l / kThiGroup], (chunk_cols[l] >> 2) + 1);
+        for (int l = 0; l < kc; ++l) thi[l / kThiGroup] = std::max(thi[l / kThiGroup], chunk_cols[l] / ne + 1);
         if (c->thi_cap < ngroups) {
           dfree(c->d_thi); c->thi_cap = 0;
           RC(dalloc(c, &c->d_thi, (size_t)ngroups + 64));
@@ -1070,10 +1078,15 @@ static int jacobian_cols_impl(hank_ctx* c, const std::vector<int>& cols, double*
       c->K_last = 0;   // policy tangents beyond the horizons were never written: not retrievable
     }
     CK(cudaMemcpyAsync(d_col_lane, col_lane.data() + col_lo, (col_hi - col_lo) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    k_ks_jac_columns<<<nblk((size_t)(col_hi - col_lo) * P), 256, 0, c->stream>>>(
-        P, d_col_ids + col_lo, col_hi - col_lo, c->alpha, c->ssKS, c->d_x, c->d_Z, d_col_lane, c->d_dKD, J + (size_t)col_lo * n);
-    c->launches++;
-    CK(cudaGetLastError());
+    if (c->eq_on)   // direct terms by a unit-seed pass through the equation programs, household term from the lanes' K̇D
+      RC(eq_residual_tangent(c, col_hi - col_lo, c->d_x, c->d_KD, c->d_Z, nullptr, d_col_ids + col_lo, c->d_dKD, d_col_lane,
+                             J + (size_t)col_lo * n));
+    else {
+      k_ks_jac_columns<<<nblk((size_t)(col_hi - col_lo) * P), 256, 0, c->stream>>>(
+          P, d_col_ids + col_lo, col_hi - col_lo, c->alpha, c->ssKS, c->d_x, c->d_Z, d_col_lane, c->d_dKD, J + (size_t)col_lo * n);
+      c->launches++;
+      CK(cudaGetLastError());
+    }
     CK(cudaStreamSynchronize(c->stream));  // host vectors are reused by the next chunk
     done_cols = col_hi;
   }
@@ -1083,7 +1096,7 @@ static int jacobian_cols_impl(hank_ctx* c, const std::vector<int>& cols, double*
 int hank_ks_jacobian_columns_dev(hank_ctx* c, int col_begin, int col_end, double* J) {
   CK(cudaSetDevice(c->device));
   if (!c->linearized) return set_error(c, HANK_ERR_STATE, "hank_ks_jacobian_columns needs a preceding hank_ks_linearize");
-  const int n = 4 * c->P;
+  const int n = c->n_endog * c->P;
   if (col_begin < 1 || col_end > n + 1 || col_end <= col_begin) return set_error(c, HANK_ERR_ARG, "bad column range");
   std::vector<int> cols(col_end - col_begin);
   for (int j = 0; j < (int)cols.size(); ++j) cols[j] = col_begin - 1 + j;
@@ -1093,7 +1106,7 @@ int hank_ks_jacobian_columns_dev(hank_ctx* c, int col_begin, int col_end, double
 int hank_ks_jacobian_column_list_dev(hank_ctx* c, int ncols, const int* cols1, double* J) {
   CK(cudaSetDevice(c->device));
   if (!c->linearized) return set_error(c, HANK_ERR_STATE, "hank_ks_jacobian_column_list needs a preceding hank_ks_linearize");
-  const int n = 4 * c->P;
+  const int n = c->n_endog * c->P;
   if (ncols < 1 || !cols1) return set_error(c, HANK_ERR_ARG, "empty column list");
   std::vector<int> cols(ncols);
   for (int j = 0; j < ncols; ++j) {
@@ -1106,7 +1119,7 @@ int hank_ks_jacobian_column_list_dev(hank_ctx* c, int ncols, const int* cols1, d
 
 int hank_ks_jacobian_column_list(hank_ctx* c, int ncols, const int* cols1, double* J) {
   CK(cudaSetDevice(c->device));
-  const size_t n = (size_t)4 * c->P;
+  const size_t n = (size_t)c->n_endog * c->P;
   if (ncols < 1) return set_error(c, HANK_ERR_ARG, "empty column list");
   RC(ensure_V(c, ncols));
   RC(hank_ks_jacobian_column_list_dev(c, ncols, cols1, c->d_JV));
@@ -1116,7 +1129,7 @@ int hank_ks_jacobian_column_list(hank_ctx* c, int ncols, const int* cols1, doubl
 
 int hank_ks_jacobian_columns(hank_ctx* c, int col_begin, int col_end, double* J) {
   CK(cudaSetDevice(c->device));
-  const size_t n = (size_t)4 * c->P;
+  const size_t n = (size_t)c->n_endog * c->P;
   if (col_end <= col_begin) return set_error(c, HANK_ERR_ARG, "bad column range");
   const int ncols = col_end - col_begin;
   RC(ensure_V(c, ncols));

@@ -44,6 +44,12 @@ struct hank_ctx {
   int Vcap = 0;
   double *h_pin = nullptr; size_t h_pin_bytes = 0;  // pinned staging for host-pointer calls
 
+  // equilibrium equations as device bytecode (hank_eq_configure, hank_eq.cu); off: the built-in Krusell-Smith block
+  bool eq_on = false;
+  int n_endog = 4, n_exog = 1, eq_ir = 2, eq_iw = 3;   // x is n_endog x P; rows of r and w; Z is n_exog x P
+  int *d_eq_off = nullptr, *d_eq_code = nullptr;
+  double *d_eq_consts = nullptr, *d_eq_ss = nullptr;
+
   // dense solve (Newton)
   void* solver = nullptr;  // cusolverDnHandle_t
   double *d_Jinv = nullptr, *d_newton = nullptr, *d_lu_work = nullptr;
@@ -130,5 +136,13 @@ void prof_end(hank_ctx* c, int kind, cudaEvent_t a);
 int set_error(hank_ctx* c, int code, const std::string& msg);
 int cuda_check(hank_ctx* c, cudaError_t e, const char* what);
 void newton_release(hank_ctx* c);   // destroys the cuSOLVER handle (hank_newton.cu)
+// generic equations (hank_eq.cu)
+int eq_extract_rw(hank_ctx* c, const double* x, double* r, double* w);
+int eq_extract_drdw(hank_ctx* c, int K, const double* V, double* dr, double* dw);
+int eq_residual(hank_ctx* c, const double* x, const double* KD, const double* Z, double* F);
+// V: [K][n] seeds, or null with unit_cols[K] (unit seed e_col per lane); dKD rows: lane l, or col_lane[l] (-1: none)
+int eq_residual_tangent(hank_ctx* c, int K, const double* x, const double* KD, const double* Z, const double* V,
+                        const int* unit_cols, const double* dKD, const int* col_lane, double* JV);
+void eq_release(hank_ctx* c);
 
 }  // namespace hank

@@ -214,23 +214,23 @@ static bool rowsplit_cfg(const hank_ctx* c, int K, TangentCfg* out) {
   else if (c->lda == 2048) { mid = TangentCfg{512, 1, 2, 4, 2, 0}; lm = 2; }   // 2 columns per exchange
   else return false;
   if (c->rs_cap[1] < 0) cm->rs_cap[1] = Sweeps<NE>::rs_max_clusters(cm, mid.NC, mid.NT, mid.L, mid.GC);
-  // (seed-horizon passes run their lanes longest first: a few clusters more than fit at once are the shortest ones and
-  // start behind the first to finish, so "one wave" may overflow by a sixth)
-  const int cap1 = c->pass_thi ? c->rs_cap[1] + c->rs_cap[1] / 6 : c->rs_cap[1];
-  if ((K + lm - 1) / lm <= cap1) { *out = mid; return true; }
+  if ((K + lm - 1) / lm <= c->rs_cap[1]) { *out = mid; return true; }
   return false;
 }
 template <int NE>
-static TangentCfg tangent_cfg(const hank_ctx* c, int K, bool allow_rowsplit = true) {
+static TangentCfg tangent_cfg(const hank_ctx* c, int K, bool allow_rowsplit = true, bool forward = false) {
   const int sm = c->sm_count;
   TangentCfg rs;
   if (allow_rowsplit && rowsplit_cfg<NE>(c, K, &rs)) return rs;
   switch (c->lda) {
     case 256: return {256, 1, K >= 4 * sm ? 4 : (K >= 2 * sm ? 2 : 1)};
     case 512: {
-      // (same slack for seed-horizon passes: 300 unit-seed lanes of a 2-GPU Jacobian build are one wave of 2-lane CTAs
-      // plus two short ones, not half a wave of 4-lane CTAs)
-      const int wave = c->pass_thi ? sm + sm / 6 : sm;
+      // Seed-horizon passes run their lanes longest first, and a BACKWARD CTA's work shrinks with its horizon: a few
+      // CTAs more than one wave are the shortest ones and start behind the first to finish (300 unit-seed lanes of a
+      // 2-GPU Jacobian build: one wave of 2-lane CTAs plus two short ones, not half a wave of 4-lane CTAs).  The
+      // forward sweep has no short CTAs (every lane runs all periods), so it keeps the strict wave; the two sweeps may
+      // use different lanes per CTA because the pass fixes the lane stride of the policy tangents (pass_Kp).
+      const int wave = (c->pass_thi && !forward) ? sm + sm / 6 : sm;
       if (K <= wave) return {512, 1, 1};
       if (K <= 2 * wave) return {512, 1, 2};
       const double c4 = cfg_cost(K, 4, sm, 1.0), c6 = cfg_cost(K, 6, sm, 1.6);
@@ -346,7 +346,7 @@ int Sweeps<NE>::backward_tangent(hank_ctx* c, int P, int K, const double* dr, co
 template <int NE>
 int Sweeps<NE>::forward_tangent(hank_ctx* c, int P, int K, const double* dpol, double* dkdpart, int* nw_out) {
   if (c->lda > 2048) return set_error(c, 1, "n_a > 2048 is not supported");
-  const TangentCfg cfg = tangent_cfg<NE>(c, K);
+  const TangentCfg cfg = tangent_cfg<NE>(c, K, true, true);
   if (cfg.NC > 0) {
     *nw_out = cfg.NC;
     const int rc = Sweeps<NE>::forward_tangent_rs(c, cfg.NC, cfg.NT, cfg.L, cfg.GC, P, K, dpol, dkdpart);

@@ -435,7 +435,7 @@ extern "C" int hank_newton_solve(hank_ctx* c, const double* Jbar, const double* 
   if (solver < 0 || solver > 2) return set_error(c, HANK_ERR_ARG, "solver must be 0 (gmres), 1 (lu) or 2 (lu, batched J(x))");
   const bool batched = solver == 2;
   if (batched) solver = 1;
-  const int P = c->P, n = 4 * P;
+  const int P = c->P, n = c->n_endog * P;
   const size_t nn = (size_t)n * n;
   // workspace
   const size_t nvec = 7, extra = (size_t)kSplit * n + 16 + (size_t)(kRestartMax + 1) * n +
@@ -486,7 +486,7 @@ extern "C" int hank_newton_solve(hank_ctx* c, const double* Jbar, const double* 
   if (!cached) CK(cudaMemcpyAsync(B.J, Jbar, nn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(B.x, x0, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(B.y, x0, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_Z, Z, P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_Z, Z, (size_t)c->n_exog * P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemsetAsync(B.H, 0, sizeof(double) * (kRestartMax + 1) * kRestartMax, c->stream));
   if (solver == 1 && !cached && getenv("HANK_CUSOLVER") == nullptr) {
     // J̅⁻¹ once: blocked Gauss-Jordan with partial pivoting (hank_dense.cu); the second half of the buffer is the

@@ -44,6 +44,7 @@ SIGNATURES = {
     "hank_get_brackets": (C.c_int, [ctx_p, C.c_int, c_i32p]),
     "hank_lottery": (C.c_int, [ctx_p, c_dp, c_i32p, c_dp]),
     "hank_ks_configure": (C.c_int, [ctx_p, C.c_double, C.c_double, C.c_double]),
+    "hank_eq_configure": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_int, C.c_int, c_ip, c_ip, C.c_int, c_dp, c_dp, c_dp]),
     "hank_ks_linearize": (C.c_int, [ctx_p, c_dp, c_dp, c_dp]),
     "hank_ks_jvp": (C.c_int, [ctx_p, C.c_int, c_dp, c_dp]),
     "hank_ks_fjvp": (C.c_int, [ctx_p, c_dp, c_dp, C.c_int, c_dp, c_dp, c_dp]),

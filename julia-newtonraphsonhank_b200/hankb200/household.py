@@ -39,6 +39,7 @@ class HouseholdBlock:
         self.n_a, self.n_e, self.T = len(self.grid), len(self.z), int(T)
         self.P = self.T - 1
         self.G = self.n_a * self.n_e
+        self.n_endog, self.n_exog = 4, 1   # the built-in Krusell-Smith block (Y, KS, r, w; Z) until eq_configure
         self.n = 4 * self.P
         self.beta, self.gamma, self.borrow_cons = float(beta), float(gamma), float(borrow_cons)
         self._h = C.c_void_p()
@@ -206,9 +207,26 @@ class HouseholdBlock:
     def ks_configure(self, alpha, delta, ss_start_KS):
         self._ck(self._L.hank_ks_configure(self._h, float(alpha), float(delta), float(ss_start_KS)))
 
+    def eq_configure(self, program, n_endog, ir, iw, ss_start, ss_end):
+        """The model's equilibrium equations as device bytecode (hankb200.equations.EquationProgram) instead of the
+        built-in Krusell-Smith block: x becomes (P, n_endog), Z (n_exog, P); `ir`, `iw` are the rows of the household
+        block's inputs r and w; ss_start / ss_end the boundary values of all variables (assemble_full_xMat)."""
+        nv = len(program.names)
+        n_exog = nv - n_endog - 1
+        if program.n_eq != n_endog:
+            raise ValueError("one equation per endogenous variable")
+        eq_off, code, consts = program.arrays()
+        ss0 = _f(ss_start, (nv,)); ss1 = _f(ss_end, (nv,))
+        self._ck(self._L.hank_eq_configure(self._h, int(n_endog), int(n_exog), int(ir), int(iw), eq_off.ctypes.data_as(c_ip),
+                                           code.ctypes.data_as(c_ip), len(program.consts), _p(consts), _p(ss0), _p(ss1)))
+        self.n_endog, self.n_exog = int(n_endog), int(n_exog)
+        self.n = self.n_endog * self.P
+
     def linearize(self, x, Z):
         """fullFunction(x): returns F(x) and keeps the linearisation for later JVPs at this x."""
-        x = _f(x, (self.n,)); Z = _f(Z, (self.P,))
+        x = _f(x, (self.n,)); Z = _f(Z).reshape(-1)
+        if Z.size != self.n_exog * self.P:
+            raise ValueError("Z must hold n_exog paths of P periods")
         F = np.empty(self.n)
         self._ck(self._L.hank_ks_linearize(self._h, _p(x), _p(Z), _p(F)))
         return F
@@ -226,7 +244,7 @@ class HouseholdBlock:
 
     def fjvp(self, x, Z, V):
         """fullFunction(x) and J(x)·V in one call: returns (F, JV)."""
-        x = _f(x, (self.n,)); Z = _f(Z, (self.P,)); V = _f(V)
+        x = _f(x, (self.n,)); Z = _f(Z).reshape(-1); V = _f(V)
         if V.ndim == 1:
             V = V[None]
         F = np.empty(self.n); JV = np.empty_like(V)

@@ -309,6 +309,55 @@ function dense_inverse(model::SequenceModel, A::AbstractMatrix{Float64})
     return out
 end
 
+# ── the model's equations as device bytecode (hank_eq_configure; the host half of compile_residuals, ModelParser.jl:217-259) ──
+const _EQ_OPS = Dict(:+ => 2, :- => 3, :* => 4, :/ => 5, :^ => 6)
+const _EQ_FUNS = Dict(:exp => 8, :log => 9, :sqrt => 10)
+function _eq_emit!(code::Vector{Cint}, consts::Vector{Float64}, ex, vidx::Dict{Symbol,Int}, params)
+    pushc(v) = (i = findfirst(==(Float64(v)), consts); i === nothing && (push!(consts, Float64(v)); i = length(consts)); append!(code, Cint[0, i - 1]))
+    if ex isa Number
+        pushc(ex)
+    elseif ex isa Symbol
+        haskey(vidx, ex) ? append!(code, Cint[1, vidx[ex], 0]) : pushc(getfield(params, ex))
+    elseif ex isa Expr && ex.head == :call
+        f, args = ex.args[1], ex.args[2:end]
+        if f isa Symbol && haskey(vidx, f) && length(args) == 1 && args[1] isa Integer      # VAR(±k)
+            append!(code, Cint[1, vidx[f], args[1]])
+        elseif f == :- && length(args) == 1
+            _eq_emit!(code, consts, args[1], vidx, params); push!(code, 7)
+        elseif haskey(_EQ_OPS, f)                                                            # n-ary: left fold like transform_expr
+            _eq_emit!(code, consts, args[1], vidx, params)
+            for a in args[2:end]
+                _eq_emit!(code, consts, a, vidx, params); push!(code, _EQ_OPS[f])
+            end
+        elseif haskey(_EQ_FUNS, f) && length(args) == 1
+            _eq_emit!(code, consts, args[1], vidx, params); push!(code, _EQ_FUNS[f])
+        else
+            error("HankB200: unsupported call $f in an equation")
+        end
+    else
+        error("HankB200: unsupported expression $ex")
+    end
+end
+"""Uploads `model.equations` as bytecode: after this call the device evaluates F, J·V and Jacobian columns of the model's own
+aggregate block (any number of endogenous / exogenous variables, lags and leads) instead of the built-in Krusell-Smith one."""
+function configure_equations!(model::SequenceModel, equations::Vector{String}, ss_start, ss_end)
+    b = _block(model)
+    names = var_names(model); endog = vars_of_type(model, :endogenous); exog = vars_of_type(model, :exogenous)
+    vidx = Dict(s => i - 1 for (i, s) in enumerate(names))
+    code = Cint[]; consts = Float64[]; off = Cint[0]
+    for eq in equations
+        parts = split(eq, "="; limit = 2)
+        length(parts) == 2 || error("Equation must contain exactly one '=': $eq")
+        _eq_emit!(code, consts, Meta.parse(strip(String(parts[1]))), vidx, model.params)
+        _eq_emit!(code, consts, Meta.parse(strip(String(parts[2]))), vidx, model.params)
+        push!(code, 3); push!(off, length(code))
+    end
+    ss0 = Float64[ss_start.vars[k] for k in names]; ss1 = Float64[ss_end.vars[k] for k in names]
+    check(b.ctx, ccall((:hank_eq_configure, LIB), Cint,
+                       (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Ptr{Cint}, Ptr{Cint}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                       b.ctx, length(endog), length(exog), vidx[:r], vidx[:w], off, code, length(consts), consts, ss0, ss1))
+end
+
 comm_unique_id() = (id = zeros(UInt8, 128); ccall((:hank_comm_unique_id, LIB), Cint, (Ptr{UInt8},), id) == 0 || error("ncclGetUniqueId failed"); id)
 comm_init(model::SequenceModel, nranks, rank, id::Vector{UInt8}) =
     (b = _block(model); check(b.ctx, ccall((:hank_comm_init, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), b.ctx, nranks, rank, id)))
