@@ -217,10 +217,10 @@ static int sw_forward_tangent(hank_ctx* c, int P, int K, const double* dpol, dou
   NE_DISPATCH(c, forward_tangent(c, P, K, dpol, dkdpart, nw));
 }
 static int sw_lanes_per_cta(hank_ctx* c, int K) { NE_DISPATCH(c, lanes_per_cta(c, K)); }
-// lane stride of the policy-tangent array for a K-lane pass: K rounded up to the lanes per CTA
+// lane stride of the policy-tangent array for a K-lane pass: K rounded up to a multiple of every lanes-per-CTA count
 static int lane_stride(hank_ctx* c, int K) {
-  const int L = std::max(1, sw_lanes_per_cta(c, K));
-  return (K + L - 1) / L * L;
+  (void)c;
+  return (K + kThiGroup - 1) / kThiGroup * kThiGroup;   // what bt_launch / ft_launch use (hank_launch.cuh)
 }
 static inline size_t bw_chunk(const hank_ctx* c) { return (size_t)52 * c->lda; }
 static inline size_t fw_chunk(const hank_ctx* c) { return (size_t)FW_NF * 8 * c->lda + (size_t)4 * (c->lda + 4); }

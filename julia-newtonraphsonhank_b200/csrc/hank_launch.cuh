@@ -214,7 +214,9 @@ static bool rowsplit_cfg(const hank_ctx* c, int K, TangentCfg* out) {
   else if (c->lda == 2048) { mid = TangentCfg{512, 1, 2, 4, 2, 0}; lm = 2; }   // 2 columns per exchange
   else return false;
   if (c->rs_cap[1] < 0) cm->rs_cap[1] = Sweeps<NE>::rs_max_clusters(cm, mid.NC, mid.NT, mid.L, mid.GC);
-  if ((K + lm - 1) / lm <= c->rs_cap[1]) { *out = mid; return true; }
+  // 2000 rows: the one-CTA kernels have no TMA ring at this size (a 106 KB column chunk), so the row-split clusters also
+  // carry passes of more than one wave of clusters (clusters are independent: the rest queue behind the resident ones)
+  if ((K + lm - 1) / lm <= c->rs_cap[1] || (c->lda == 2048 && c->rs_cap[1] > 0)) { *out = mid; return true; }
   return false;
 }
 template <int NE>
@@ -240,7 +242,9 @@ static TangentCfg tangent_cfg(const hank_ctx* c, int K, bool allow_rowsplit = tr
     case 1024: {
       if (K <= sm) return {512, 2, 1};
       const double c2 = cfg_cost(K, 2, sm, 1.0), c3 = cfg_cost(K, 3, sm, 1.6);
-      if (c3 < c2 && !c->no_wide) return {256, 4, 3};
+      // (the 3-lane shape only pays off backward: its forward kernel, 4 rows x 3 lanes fully unrolled at 255 registers,
+      // stalls on instruction fetch — 6.6 vs 4.5 ms at K = 444, profiles/r02_notes.md; the lane stride is common)
+      if (c3 < c2 && !c->no_wide && !forward) return {256, 4, 3};
       return {512, 2, 2};
     }
     default: return {512, 4, 1};
@@ -254,7 +258,7 @@ static int bt_launch(hank_ctx* c, int P, int K, const double* dr, const double* 
                      double* dpol, double* dvf) {
   const Consts<NE> M = make_consts<NE>(c, P);
   const int grid = (K + L - 1) / L;
-  const int Kp = c->pass_Kp ? c->pass_Kp : grid * L;   // lane stride of the policy tangents (>= grid * L)
+  const int Kp = c->pass_Kp ? c->pass_Kp : (K + kThiGroup - 1) / kThiGroup * kThiGroup;   // lane stride of the policy tangents: every lanes-per-CTA count divides 12, so the two sweeps may differ in theirs
   c->Kp_last = Kp; c->dpol_rs = false;
   constexpr int LDA = NT * R;
   // one ring slot per income state (compile-time slot addresses, hank_tangent_tma.cuh) where the n_e chunks fit
@@ -284,7 +288,7 @@ template <int NE, int R, int NT, int L>
 static int ft_launch(hank_ctx* c, int P, int K, const double* dpol, double* dkdpart) {
   const Consts<NE> M = make_consts<NE>(c, P);
   const int grid = (K + L - 1) / L;
-  const int Kp = c->pass_Kp ? c->pass_Kp : grid * L;
+  const int Kp = c->pass_Kp ? c->pass_Kp : (K + kThiGroup - 1) / kThiGroup * kThiGroup;
   constexpr int LDA = NT * R;
   if constexpr (LDA <= 1024) if (!c->no_tma) {
     const size_t slot = fw_chunk_bytes<LDA>() + (size_t)L * LDA * 8;

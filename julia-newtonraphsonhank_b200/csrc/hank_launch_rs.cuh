@@ -55,7 +55,7 @@ static int ft_rs_launch(hank_ctx* c, int P, int K, const double* dpol, double* d
   const int ncl = (K + L - 1) / L;
   // ṗ comes from this pass's row-split backward sweep (same shape), or from the caller in the column-major layout
   const bool pd_rs = c->dpol_rs && c->dpol_rs_L == L && c->dpol_rs_NC == NC && c->dpol_rs_ncl == ncl;
-  const int Kp = c->pass_Kp ? c->pass_Kp : ncl * L;
+  const int Kp = c->pass_Kp ? c->pass_Kp : (K + kThiGroup - 1) / kThiGroup * kThiGroup;   // (the caller-layout stride of hank_forward_policies)
   const size_t slot = (size_t)GC * rs_fw_col_bytes<NT, L>();
   const int S = rs_ring_slots(c, rs_fw_smem<NT, L, GC, LA>(0), slot + 16, LA + 2, GC == 1 ? 3 * NE : 6);
   if (S < LA + 2) return -1;
