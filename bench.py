@@ -413,6 +413,23 @@ def main():
     if strong:
         out["jacobian_build_strong_scaling"] = strong
 
+    # ---- N = 1: the few-lane regimes of SURVEY 8d (one JVP = direction x full sweep pair, at a fixed linearisation) ---
+    if world == 1 and not synth:
+        reg = {}
+        blk._ck(L.hank_ks_linearize_dev(h, vp(xd), vp(Zd), vp(Fd)))
+        for kk in (1, 64):
+            if kk > K:
+                continue
+            for _ in range(3):
+                blk._ck(L.hank_ks_jvp_dev(h, kk, vp(Vd), vp(JVd)))
+            blk.sync(); blk.timer_start()
+            for _ in range(20):
+                blk._ck(L.hank_ks_jvp_dev(h, kk, vp(Vd), vp(JVd)))
+            t_ms = blk.timer_stop() / 20
+            reg["K%d" % kk] = {"ms_per_pass": t_ms, "jvps_per_sec": kk / (t_ms * 1e-3)}
+        out["jvp_regimes"] = dict(reg, note="K-lane JVP passes at a fixed linearisation (tape resident), CUDA events, mean of 20: "
+                                            "K=1 is Newton's inner JVP, K=64 the batched stress of BASELINE config 5")
+
     # ---- N = 1: the metric's other halves — Jacobian build and ms per Newton solve, CPU beside them ---
     if world == 1 and not synth and not args.no_newton:
         ones = np.ones(P)

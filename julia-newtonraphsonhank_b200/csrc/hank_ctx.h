@@ -83,7 +83,8 @@ struct hank_ctx {
   int rs_cap[2] = {-1, -1};      // resident clusters of the 1-lane / 4-lane row-split shape (-1: not asked yet)
   // row-block-major copies of the tape for the row-split kernels, and the layout of the policy tangents in d_dpol
   unsigned char *tape_rs_bw = nullptr, *tape_rs_fw = nullptr;
-  bool tape_rs_bw_valid = false, tape_rs_fw_valid = false;
+  int tape_rs_bw_nt = 0, tape_rs_fw_nt = 0;   // rows per block the copies were made for (0: stale; a pass with another
+                                              // cluster shape at the same linearisation has to remake them)
   bool dpol_rs = false; int dpol_rs_L = 0, dpol_rs_NC = 0, dpol_rs_ncl = 0;   // d_dpol is [t][cluster][rank][e][l][NT]
   int Kp_last = 0;               // lane stride of the policy tangents written by the last backward tangent sweep
   // Seed horizons of the pass in flight (hank_ks_jacobian_columns): lanes come in groups of kThiGroup

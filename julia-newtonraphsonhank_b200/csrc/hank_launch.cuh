@@ -99,7 +99,7 @@ static int launch_cluster_grid(hank_ctx* c, int kind, KernelT kern, int grid, in
 template <int NE, int R, int NT>
 static int bp_launch(hank_ctx* c, int P, const double* valueT, const double* r, const double* w) {
   const Consts<NE> M = make_consts<NE>(c, P);
-  c->tape_rs_bw_valid = false;
+  c->tape_rs_bw_nt = 0;
   // exchange through distributed shared memory (hank_primal_dsmem.cuh); with two or more rows per thread the
   // per-row remote stores cost more than the fence they replace (1000x7: 4.16 vs 3.97 us per period)
   if constexpr (R == 1) if (!c->no_cluster && !c->no_dsmem && NE > 1 && bp_ds_smem<NE, NT * R>() <= (size_t)c->smem_max) {
@@ -140,7 +140,7 @@ int Sweeps<NE>::backward_primal(hank_ctx* c, int P, const double* valueT, const 
 template <int NE, int R, int NT, int CS>
 static int fp_launch(hank_ctx* c, int P, const double* D0, const double* pol, double* KD) {
   const Consts<NE> M = make_consts<NE>(c, P);
-  c->tape_rs_fw_valid = false;
+  c->tape_rs_fw_nt = 0;
   constexpr int LDA = NT * R;
   if (!c->no_cluster && !c->no_dsmem && NE > 1 && CS == NE && fp_ds_smem<NE, LDA>() <= (size_t)c->smem_max) {
     int rc = launch_cluster<NE>(c, KIND_FP, k_forward_primal_ds<NE, R, NT>, NT, fp_ds_smem<NE, LDA>(), "k_forward_primal_ds", M,

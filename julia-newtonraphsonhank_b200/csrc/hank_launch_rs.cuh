@@ -12,10 +12,12 @@ static int rs_ring_slots(const hank_ctx* c, size_t fixed, size_t slot, int min_s
   const int s = (int)(((size_t)c->smem_max - fixed) / slot);
   return s > max_slots ? max_slots : s;
 }
-// Row-block-major copies of the tape (k_tape_rowblocks_*), made once per linearisation on first use.
+// Row-block-major copies of the tape (k_tape_rowblocks_*), made on first use per linearisation and block size NT
+// (a K = 1 pass after a K = 64 pass at the same linearisation uses another cluster shape, hence another layout).
 static int ensure_tape_rs(hank_ctx* c, int P, int NT, bool forward) {
   const size_t ncols = (size_t)c->P_alloc * c->n_e;
-  const size_t bwb = ncols * 52 * (size_t)c->lda, fwb = ncols * (36 * (size_t)c->lda + 16 * (size_t)(c->lda / NT));
+  // (sized for the smallest block any shape uses, 32 rows: the forward copy carries 4 extra range starts per block)
+  const size_t bwb = ncols * 52 * (size_t)c->lda, fwb = ncols * (36 * (size_t)c->lda + 16 * (size_t)(c->lda / 32));
   if (!c->tape_rs_bw) {
     int rc = cuda_check(c, cudaMalloc((void**)&c->tape_rs_bw, bwb), "cudaMalloc(tape_rs_bw)");
     if (rc) return rc;
@@ -24,13 +26,13 @@ static int ensure_tape_rs(hank_ctx* c, int P, int NT, bool forward) {
   }
   const size_t n = (size_t)P * c->n_e * c->lda;
   const unsigned grid = (unsigned)((n + 255) / 256);
-  if (!forward && !c->tape_rs_bw_valid) {
+  if (!forward && c->tape_rs_bw_nt != NT) {
     k_tape_rowblocks_bw<<<grid, 256, 0, c->stream>>>(c->tape.bw, c->tape_rs_bw, P * c->n_e, c->n_e, c->lda, NT);
-    c->launches++; c->tape_rs_bw_valid = true;
+    c->launches++; c->tape_rs_bw_nt = NT;
   }
-  if (forward && !c->tape_rs_fw_valid) {
+  if (forward && c->tape_rs_fw_nt != NT) {
     k_tape_rowblocks_fw<<<grid, 256, 0, c->stream>>>(c->tape.fw, c->tape_rs_fw, P * c->n_e, c->n_e, c->lda, NT);
-    c->launches++; c->tape_rs_fw_valid = true;
+    c->launches++; c->tape_rs_fw_nt = NT;
   }
   return cuda_check(c, cudaGetLastError(), "k_tape_rowblocks");
 }

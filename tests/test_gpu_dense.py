@@ -20,7 +20,7 @@ def blk():
     b.close()
 
 
-@pytest.mark.parametrize("n", [1, 2, 5, 16, 17, 31, 32, 100, 299, 1196, 1700, 2500])
+@pytest.mark.parametrize("n", [1, 2, 5, 16, 17, 31, 32, 100, 299, 1196, 1700, 2500, 3301])   # block widths 16 (n <= ~1750), 8, 4
 def test_inverse_matches_lapack(blk, n):
     rng = np.random.default_rng(n)
     A = rng.standard_normal((n, n))

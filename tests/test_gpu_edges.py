@@ -287,3 +287,27 @@ def test_full_size_properties_2000x11_T500():
     _, d3 = blk.block(s["r"], s["w"], dr3, dw3)
     assert close(d3[2], 2 * d3[0] - d3[1], rtol=1e-9, atol=1e-11)
     blk.close()
+
+
+def test_lane_counts_in_any_order_at_one_linearisation():
+    """Passes of different lane counts at the SAME linearisation use different cluster shapes, hence different
+    row-block layouts of the tape copy: every order must give the same columns (regression: a K = 1 pass after a
+    K = 64 pass read the 256-row layout with the 64-row kernel and trapped)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ss_500x7_T300.npz"))
+    from hankb200 import HouseholdBlock
+    T = int(g["T"]); P = T - 1; n = 4 * P
+    blk = HouseholdBlock(g["grid"], g["z"], g["Pi"], float(g["beta"]), float(g["gamma"]), float(g["borrow_cons"]), T)
+    blk.set_terminal(g["ss_value"]); blk.set_initial_dist(g["ss_D"])
+    blk.ks_configure(float(g["alpha"]), float(g["delta"]), float(g["ss_vars"][1]))
+    x0 = np.tile(g["ss_vars"][:4], P); Z = 1.0 + 0.8 ** np.arange(1, P + 1)
+    V = np.random.default_rng(11).standard_normal((300, n))
+    blk.linearize(x0, Z)
+    first = {}
+    for K in (64, 1, 300, 4, 64, 18, 1, 150):
+        JV = blk.jvp(V[:K])
+        assert np.all(np.isfinite(JV))
+        if K in first:
+            assert np.array_equal(JV, first[K]), K
+        first[K] = JV
+        assert close(JV[0], first[64][0], rtol=1e-9), (K, maxerr(JV[0], first[64][0]))   # lane 0 whatever the shape
+    blk.close()
