@@ -1,6 +1,7 @@
 // hank_launch_rs.cuh — launchers of the row-split cluster tangent sweeps (hank_tangent_rowsplit.cuh), templated
 // on n_e.  Included only by hank_ne*_rs.cu so that these kernels compile in their own translation units.
 #pragma once
+#include <cstdlib>
 #include "hank_launch.cuh"
 #include "hank_tangent_rowsplit.cuh"
 
@@ -59,6 +60,19 @@ static int ft_rs_launch(hank_ctx* c, int P, int K, const double* dpol, double* d
   const bool pd_rs = c->dpol_rs && c->dpol_rs_L == L && c->dpol_rs_NC == NC && c->dpol_rs_ncl == ncl;
   const int Kp = c->pass_Kp ? c->pass_Kp : (K + kThiGroup - 1) / kThiGroup * kThiGroup;   // (the caller-layout stride of hank_forward_policies)
   const size_t slot = (size_t)GC * rs_fw_col_bytes<NT, L>();
+  // one lane, a whole period per exchange: a thread per (income state, row) instead of per row (hank_tangent_rowsplit.cuh)
+  if constexpr (L == 1 && GC == NE && LA == 0 && NE * NT + 32 <= 1024) {
+    static const bool no_ce = getenv("HANK_NO_RS_CE") != nullptr;
+    const int Sc = rs_ring_slots(c, rs_fw_ce_smem<NE, NT>(0), slot + 16, 2, 6);
+    if (!no_ce && Sc >= 2) {
+      int rc = ensure_tape_rs(c, P, NT, true);
+      if (rc) return rc;
+      rc = launch_cluster_grid(c, KIND_FT, k_forward_tangent_rs_ce<NE, NC, NT>, ncl * NC, NC, NE * NT + 32, rs_fw_ce_smem<NE, NT>(Sc),
+                               "k_forward_tangent_rs_ce", M, (const unsigned char*)c->tape_rs_fw, K, Kp, Sc, c->pass_thi,
+                               (const double*)c->d_zero, dpol, pd_rs ? 1 : 0, dkdpart);
+      if (rc >= 0) return rc;   // (-1: this cluster cannot be scheduled with the larger CTAs; use the kernel below)
+    }
+  }
   const int S = rs_ring_slots(c, rs_fw_smem<NT, L, GC, LA>(0), slot + 16, LA + 2, GC == 1 ? 3 * NE : 6);
   if (S < LA + 2) return -1;
   int rc = ensure_tape_rs(c, P, NT, true);

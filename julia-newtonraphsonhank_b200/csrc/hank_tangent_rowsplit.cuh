@@ -555,6 +555,158 @@ k_forward_tangent_rs(const Consts<NE> M, const unsigned char* __restrict__ tape_
 }
 
 // ======================================================================================
+// Forward tangent sweep of ONE lane per cluster with a thread per (income state, row) instead of per row.
+//
+// In the latency shapes (one lane, a whole period per exchange) the kernel above gives a CTA NT/32 compute warps —
+// one per scheduler at 64 rows — and each of them walks all n_e columns of its rows: ~585 dependent-latency
+// instructions per warp and period (profiles/r02_notes.md: 4.2 M warp instructions for 299 periods on 8 CTAs, issue
+// slots 17 % busy), i.e. 1.84 us per period whatever the hardware could overlap.  Here the n_e columns of a row go to
+// n_e different warps (thread = (e, row), NE*NT threads + the producer warp), so a warp's chain per period is one
+// column (~70 instructions) and four to seven warps share a scheduler.  The price is the Markov mix: the post-lottery
+// masses of a row meet through shared memory (one more named barrier per period) and every thread forms the mixed
+// mass of its own income state.  Everything else — ring, producer warp, exchange buffers, hand-shake, DSMEM pulls,
+// summation order within a column — is the kernel above with L = 1, GC = NE, LA = 0.
+// smem: ring[S][ NE x (4 fields x NT doubles | NT+4 ints) | ṗ [NE][NT] ] | xy[2][2][NE][NT] | mix[NE][NT] |
+//       red[2][NE*NT/32] | full[S] | empty[S] | ready[2]
+// ======================================================================================
+template <int NE, int NT>
+constexpr size_t rs_fw_ce_smem(int S) {
+  return (size_t)S * NE * rs_fw_col_bytes<NT, 1>() + (size_t)2 * 2 * NE * NT * 8 + (size_t)NE * NT * 8 + (size_t)2 * (NE * NT / 32) * 8 +
+         (size_t)(2 * S + 2) * 8 + 128;
+}
+template <int NE, int NC, int NT>
+__global__ void __launch_bounds__(NE * NT + 32, 1)
+k_forward_tangent_rs_ce(const Consts<NE> M, const unsigned char* __restrict__ tape_rs, int K, int Kp, int S,
+                        const int* __restrict__ thi, const double* __restrict__ zeros, const double* __restrict__ dpol,
+                        int pd_rs, double* __restrict__ dkdpart) {
+  constexpr int LDA = NC * NT, NB = 2, NTC = NE * NT, NWC = NTC / 32;
+  constexpr int COLB = (int)rs_fw_tape_col_bytes<NT>(), COLD = COLB / 8;
+  constexpr int ST_OFF = FW_NF * NT, PD_OFF = NE * COLD, SLOTD = NE * COLD + NE * NT, XYD = NE * NT;
+  static_assert(NT % 32 == 0, "a warp must not straddle two income states");
+  extern __shared__ __align__(128) unsigned char smem_rs[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_rank();
+  const int cluster = blockIdx.x / NC, ncl = gridDim.x / NC;
+  const int lane0 = cluster;
+  const int P = M.P;
+  double* ring = reinterpret_cast<double*>(smem_rs);
+  double* xy = ring + (size_t)S * SLOTD;
+  double* mix = xy + (size_t)NB * 2 * XYD;
+  double* red = mix + XYD;
+  uint64_t* full = reinterpret_cast<uint64_t*>(red + 2 * NWC);
+  uint64_t* empty = full + S;
+  uint64_t* ready = empty + S;
+  const uint32_t xy_s = smem_u32(xy);
+  const int pe = thi ? min(P, thi[lane0 / kThiGroup]) : P;   // ṗ is zero (and unwritten) from period pe on
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWC); }
+    for (int b = 0; b < NB; ++b) mbar_init(&ready[b], NC);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  cluster_sync_all();
+
+  if (warp == NWC) {
+    // ---- producer warp: the period's tape columns of this CTA's rows (one piece) and ṗ of the lane
+    Cursor cs;
+    for (int t = 0; t < P; ++t) {
+      double* dst = ring + (size_t)cs.i * SLOTD;
+      constexpr uint32_t PDB = (uint32_t)(NE * NT * 8);
+      if (lane == 0) {
+        if (t >= S) mbar_wait(&empty[cs.i], cs.par ^ 1);
+        mbar_expect_tx(&full[cs.i], (uint32_t)(NE * COLB) + PDB);
+        bulk_g2s(dst, tape_rs + (((size_t)t * NC + rank) * NE) * COLB, (uint32_t)(NE * COLB), &full[cs.i]);
+        if (t >= pe) {
+          for (uint32_t o = 0; o < PDB; o += kZeroBytes)
+            bulk_g2s(dst + PD_OFF + o / 8, zeros, min(PDB - o, (uint32_t)kZeroBytes), &full[cs.i]);
+        } else if (pd_rs) {
+          bulk_g2s(dst + PD_OFF, dpol + ((((size_t)t * ncl + cluster) * NC + rank) * NE) * NT, PDB, &full[cs.i]);
+        }
+      }
+      __syncwarp();
+      if (t < pe && !pd_rs)
+        for (int i = lane; i < NE; i += 32)
+          bulk_g2s(dst + PD_OFF + (size_t)i * NT, dpol + ((((size_t)t * NE + i) * Kp + lane0) * LDA + rank * NT), NT * 8, &full[cs.i]);
+      cs.next(S);
+    }
+  } else {
+    const int e = tid / NT, row = tid - e * NT;   // (warp-uniform e)
+    double pic[NE];                               // Π[·, e]: this thread forms the mixed mass of income state e
+#pragma unroll
+    for (int e1 = 0; e1 < NE; ++e1) pic[e1] = M.Pi[e1][e];
+    double Dd = 0.0;
+    uint32_t rdy_remote = 0;
+    if (tid < NC) rdy_remote = map_to_cta(smem_u32(ready), (uint32_t)tid);
+    Cursor sl_c, b_c;
+    for (int t = 0; t < P; ++t) {
+      // ---- A: lottery masses ẋ, ẏ of this (row, income state)
+      const double* sl = ring + (size_t)sl_c.i * SLOTD;
+      double* xw = xy + (size_t)b_c.i * 2 * XYD;
+      mbar_wait(&full[sl_c.i], sl_c.par);
+      const double pd = sl[PD_OFF + e * NT + row];
+      const double om = sl[e * COLD + FW_OM * NT + row], dco = sl[e * COLD + FW_DCO * NT + row];
+      const double Dn = sl[e * COLD + FW_D * NT + row], pv = sl[e * COLD + FW_P * NT + row];
+      const int* sst = reinterpret_cast<const int*>(sl + e * COLD + ST_OFF) + row + 1;
+      const int s0 = sst[0], s1 = sst[1], s2 = sst[2];
+      const double xd = fma(om, Dd, dco * pd);
+      xw[e * NT + row] = xd;
+      xw[XYD + e * NT + row] = Dd - xd;
+      double kacc = pd * Dn;
+      named_bar_sync(1, NTC);
+      if (tid < NC) mbar_arrive_remote(rdy_remote + 8u * b_c.i);
+      if (t > 0 && tid == 0 && lane0 < K) {   // the previous period's K̇D share of this CTA
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NWC; ++w) s += red[((t - 1) & 1) * NWC + w];
+        dkdpart[((size_t)lane0 * P + (t - 1)) * NC + rank] = s;
+      }
+      // ---- B: the sources of this destination row, pulled from their owners
+      const double* xr_l = xw;
+      const uint32_t xr_s = xy_s + (uint32_t)(b_c.i * 2 * XYD) * 8u;
+      mbar_wait(&ready[b_c.i], b_c.par);
+      double xv[2][1], yv[2][1];
+      gather_rs_first<1, NT, false>(xr_l + e * NT, xr_l + XYD + e * NT, xr_s + (uint32_t)(e * NT) * 8u,
+                                    xr_s + (uint32_t)(XYD + e * NT) * 8u, s0, s1, s2, rank, xv, yv);
+      double acc[1];
+      {   // 0 + x0 + y0 + x1 + y1: the order of gather_row's predicated chain
+        const int n1 = s1 - s0, n2 = s2 - s1;
+        double a = n1 > 0 ? xv[0][0] : 0.0;
+        if (n2 > 0) a += yv[0][0];
+        if (n1 > 1) a += xv[1][0];
+        if (n2 > 1) a += yv[1][0];
+        acc[0] = a;
+      }
+      gather_rs_rest<1, NT, false>(xr_l + e * NT, xr_l + XYD + e * NT, xr_s + (uint32_t)(e * NT) * 8u,
+                                   xr_s + (uint32_t)(XYD + e * NT) * 8u, s0, s1, s2, rank, lane, acc);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_local(&empty[sl_c.i]);   // the tape slot goes back to the producer
+      // ---- Markov mix across the income states of the row (through shared memory) and <p_t, Ḋ_t>
+      mix[e * NT + row] = acc[0];
+      named_bar_sync(2, NTC);
+      double d = 0.0;
+#pragma unroll
+      for (int e1 = 0; e1 < NE; ++e1) d = fma(pic[e1], mix[e1 * NT + row], d);
+      Dd = d;
+      kacc = fma(pv, d, kacc);
+      const double s = warp_sum(kacc);
+      if (lane == 0) red[(t & 1) * NWC + warp] = s;
+      sl_c.next(S); b_c.next(NB);
+    }
+    named_bar_sync(1, NTC);
+    if (tid == 0 && lane0 < K && P > 0) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < NWC; ++w) s += red[((P - 1) & 1) * NWC + w];
+      dkdpart[((size_t)lane0 * P + (P - 1)) * NC + rank] = s;
+    }
+  }
+  __syncwarp();
+  cluster_sync_all();
+}
+
+// ======================================================================================
 // Row-block-major copies of the primal tape for the kernels above (see the header comment).
 // One thread per (column, row): the row's coefficients and index / range start.
 // ======================================================================================
