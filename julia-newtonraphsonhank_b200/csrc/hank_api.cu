@@ -359,28 +359,50 @@ static int tangent_pass(hank_ctx* c, int P, int K) {
   const int* thi = c->pass_thi;
   const int Kp_all = c->pass_Kp;
   double* dpol2 = c->d_dpol + (size_t)P * c->n_e * (size_t)K1 * c->lda;   // policy tangents of the lanes beyond the cut
-  if (K1 < K) c->pass_Kp = K1;
-  RC(tangent_pass_range(c, P, K1, 0, c->d_dpol));
-  if (K1 < K) {
-    c->pass_thi = thi + K1 / kThiGroup;
-    RC(tangent_pass_range(c, P, K - K1, K1, dpol2));
-    c->pass_thi = thi;
+  if (K1 == K) {
+    RC(tangent_pass_range(c, P, K, 0, c->d_dpol));
+    RC(join_side(c));  // the forward tangent needs the forward tape of the linearisation
+    int nw = 16;
+    RC(sw_forward_tangent(c, P, K, c->d_dpol, c->d_dkdpart, &nw));
+    k_reduce_partials<<<nblk((size_t)K * P), 256, 0, c->stream>>>(c->d_dkdpart, nw, K * P, c->d_dKD);
+    c->launches++;
+    return cuda_check(c, cudaGetLastError(), "k_reduce_partials");
   }
-  RC(join_side(c));  // the forward tangent needs the forward tape of the linearisation
+  // The overflow lanes run on the copy stream NEXT TO the main wave instead of behind it: the main backward sweep's
+  // CTAs are sorted longest horizon first, so SMs free up from half its duration on, and the handful of 8-CTA
+  // clusters does both of its sweeps in that tail (0.25 + 0.39 ms at 500x7) before the main forward sweep needs
+  // every SM again.
+  cudaStream_t main_s = c->stream;
+  CK(cudaEventRecord(c->ev_v, main_s));                   // seeds, horizons and the backward tape are in place
+  CK(cudaStreamWaitEvent(c->stream3, c->ev_v, 0));
+  c->pass_Kp = K1;
+  RC(tangent_pass_range(c, P, K1, 0, c->d_dpol));         // main wave, backward
+  double* part2 = c->d_dkdpart + (size_t)K1 * P * 16;
+  c->stream = c->stream3;
+  c->pass_thi = thi + K1 / kThiGroup;
+  int rc = tangent_pass_range(c, P, K - K1, K1, dpol2);   // overflow lanes, backward
+  if (rc == HANK_OK && c->fp_pending) rc = cuda_check(c, cudaStreamWaitEvent(c->stream3, c->ev_fp, 0), "cudaStreamWaitEvent");
+  int nw2 = 16;
+  if (rc == HANK_OK) rc = sw_forward_tangent(c, P, K - K1, dpol2, part2, &nw2);   // overflow lanes, forward
+  if (rc == HANK_OK) {
+    k_reduce_partials<<<nblk((size_t)(K - K1) * P), 256, 0, c->stream>>>(part2, nw2, (K - K1) * P, c->d_dKD + (size_t)K1 * P);
+    c->launches++;
+    rc = cuda_check(c, cudaGetLastError(), "k_reduce_partials");
+  }
+  if (rc == HANK_OK) rc = cuda_check(c, cudaEventRecord(c->ev_x, c->stream3), "cudaEventRecord");
+  c->stream = main_s;
+  c->pass_thi = thi;
+  if (rc != HANK_OK) { c->pass_Kp = Kp_all; return rc; }
+  rc = join_side(c);
   int nw = 16;
-  RC(sw_forward_tangent(c, P, K1, c->d_dpol, c->d_dkdpart, &nw));
+  if (rc == HANK_OK) rc = sw_forward_tangent(c, P, K1, c->d_dpol, c->d_dkdpart, &nw);   // main wave, forward
+  c->pass_Kp = Kp_all;
+  RC(rc);
   k_reduce_partials<<<nblk((size_t)K1 * P), 256, 0, c->stream>>>(c->d_dkdpart, nw, K1 * P, c->d_dKD);
   c->launches++;
-  if (K1 < K) {
-    double* part2 = c->d_dkdpart + (size_t)K1 * P * 16;
-    c->pass_thi = thi + K1 / kThiGroup;
-    int rc = sw_forward_tangent(c, P, K - K1, dpol2, part2, &nw);
-    c->pass_thi = thi; c->pass_Kp = Kp_all;
-    RC(rc);
-    k_reduce_partials<<<nblk((size_t)(K - K1) * P), 256, 0, c->stream>>>(part2, nw, (K - K1) * P, c->d_dKD + (size_t)K1 * P);
-    c->launches++;
-  }
-  return cuda_check(c, cudaGetLastError(), "k_reduce_partials");
+  CK(cudaGetLastError());
+  CK(cudaStreamWaitEvent(main_s, c->ev_x, 0));            // the overflow lanes' K̇D before anyone reads d_dKD
+  return HANK_OK;
 }
 
 }  // namespace hank
@@ -440,6 +462,7 @@ int hank_ctx_create(hank_ctx** out, int device, int n_a, int n_e, int T, const d
   { const char* nt = getenv("HANK_NO_ROWSPLIT"); c->no_rowsplit = nt && nt[0] == '1'; }
   { const char* nt = getenv("HANK_NO_RING_NE"); c->no_ring_ne = nt && nt[0] == '1'; }
   { const char* nt = getenv("HANK_RS_MAXK"); c->rs_max_k = nt ? atoi(nt) : 0; }
+  { const char* nt = getenv("HANK_RS_RELAXED"); c->rs_relaxed = nt && nt[0] == '1'; }
   { const char* nt = getenv("HANK_RS_NO_MULTI"); c->rs_no_multi = nt && nt[0] == '1'; }
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   {
@@ -450,6 +473,7 @@ int hank_ctx_create(hank_ctx** out, int device, int n_a, int n_e, int T, const d
     CK(cudaEventCreateWithFlags(&c->ev_fp, cudaEventDisableTiming));
     CK(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->ev_v, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_x, cudaEventDisableTiming));
     const char* nv = getenv("HANK_NO_OVERLAP"); c->no_overlap = nv && nv[0] == '1';
   }
   CK(cudaEventCreate(&c->ev0));
@@ -486,6 +510,7 @@ void hank_ctx_destroy(hank_ctx* c) {
   if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
   if (c->stream3) { cudaStreamSynchronize(c->stream3); cudaStreamDestroy(c->stream3); }
   if (c->ev_v) cudaEventDestroy(c->ev_v);
+  if (c->ev_x) cudaEventDestroy(c->ev_x);
   if (c->ev_bp) cudaEventDestroy(c->ev_bp);
   if (c->ev_fp) cudaEventDestroy(c->ev_fp);
   hank_comm_destroy(c);

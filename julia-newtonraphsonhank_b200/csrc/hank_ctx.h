@@ -17,7 +17,7 @@ struct hank_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;   // high-priority side stream: forward primal sweep overlapping the backward tangent
   cudaStream_t stream3 = nullptr;   // copy stream: tangent seeds upload overlapping the primal sweep
-  cudaEvent_t ev_bp = nullptr, ev_fp = nullptr, ev_v = nullptr;
+  cudaEvent_t ev_bp = nullptr, ev_fp = nullptr, ev_v = nullptr, ev_x = nullptr;   // ev_x: overflow lanes of a Jacobian pass done (stream3)
   bool fp_pending = false, no_overlap = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int smem_max = 0, sm_count = 0;
@@ -78,6 +78,7 @@ struct hank_ctx {
   bool no_skip = false;          // HANK_NO_SKIP=1: unit-seed Jacobian lanes sweep all periods
   bool no_ring_ne = false;       // HANK_NO_RING_NE=1: backward tangent always through the runtime-sized ring
   bool no_rowsplit = false;      // HANK_NO_ROWSPLIT=1: never split a lane group's rows over a cluster
+  bool rs_relaxed = false;       // HANK_RS_RELAXED=1: relaxed cluster hand-shakes in the row-split kernels (racy; A/B only)
   bool rs_no_multi = false;      // HANK_RS_NO_MULTI=1: no multi-lane row-split clusters (mid lane counts run one CTA per lane)
   int rs_max_k = 0;              // HANK_RS_MAXK: lane count up to which 1-lane row-split clusters are used (0: sm_count / NC)
   int rs_cap[2] = {-1, -1};      // resident clusters of the 1-lane / 4-lane row-split shape (-1: not asked yet)

@@ -48,9 +48,9 @@ static int bt_rs_launch(hank_ctx* c, int P, int K, const double* dr, const doubl
   if (S < LA + 2) return -1;
   int rc = ensure_tape_rs(c, P, NT, false);
   if (rc) return rc;
-  return launch_cluster_grid(c, KIND_BT, k_backward_tangent_rs<NE, NC, NT, L, GC, LA>, ncl * NC, NC, NT + 32,
+  return launch_cluster_grid(c, KIND_BT, k_backward_tangent_rs<NE, NC, NT, L, GC, LA>, ncl * NC, NC, NT + 64,
                              rs_bw_smem<NT, L, GC, LA>(S), "k_backward_tangent_rs", M, c->tape, (const unsigned char*)c->tape_rs_bw, K, S,
-                             c->pass_thi, dr, dw, dpol);
+                             c->pass_thi, dr, dw, dpol, c->rs_relaxed ? 0 : 1);
 }
 template <int NE, int NC, int NT, int L, int GC, int LA>
 static int ft_rs_launch(hank_ctx* c, int P, int K, const double* dpol, double* dkdpart) {
@@ -61,15 +61,15 @@ static int ft_rs_launch(hank_ctx* c, int P, int K, const double* dpol, double* d
   const int Kp = c->pass_Kp ? c->pass_Kp : (K + kThiGroup - 1) / kThiGroup * kThiGroup;   // (the caller-layout stride of hank_forward_policies)
   const size_t slot = (size_t)GC * rs_fw_col_bytes<NT, L>();
   // one lane, a whole period per exchange: a thread per (income state, row) instead of per row (hank_tangent_rowsplit.cuh)
-  if constexpr (L == 1 && GC == NE && LA == 0 && NE * NT + 32 <= 1024) {
+  if constexpr (L == 1 && GC == NE && LA == 0 && NE * NT + 64 <= 1024) {
     static const bool no_ce = getenv("HANK_NO_RS_CE") != nullptr;
     const int Sc = rs_ring_slots(c, rs_fw_ce_smem<NE, NT>(0), slot + 16, 2, 6);
     if (!no_ce && Sc >= 2) {
       int rc = ensure_tape_rs(c, P, NT, true);
       if (rc) return rc;
-      rc = launch_cluster_grid(c, KIND_FT, k_forward_tangent_rs_ce<NE, NC, NT>, ncl * NC, NC, NE * NT + 32, rs_fw_ce_smem<NE, NT>(Sc),
+      rc = launch_cluster_grid(c, KIND_FT, k_forward_tangent_rs_ce<NE, NC, NT>, ncl * NC, NC, NE * NT + 64, rs_fw_ce_smem<NE, NT>(Sc),
                                "k_forward_tangent_rs_ce", M, (const unsigned char*)c->tape_rs_fw, K, Kp, Sc, c->pass_thi,
-                               (const double*)c->d_zero, dpol, pd_rs ? 1 : 0, dkdpart);
+                               (const double*)c->d_zero, dpol, pd_rs ? 1 : 0, dkdpart, c->rs_relaxed ? 0 : 1);
       if (rc >= 0) return rc;   // (-1: this cluster cannot be scheduled with the larger CTAs; use the kernel below)
     }
   }
@@ -77,9 +77,9 @@ static int ft_rs_launch(hank_ctx* c, int P, int K, const double* dpol, double* d
   if (S < LA + 2) return -1;
   int rc = ensure_tape_rs(c, P, NT, true);
   if (rc) return rc;
-  return launch_cluster_grid(c, KIND_FT, k_forward_tangent_rs<NE, NC, NT, L, GC, LA>, ncl * NC, NC, NT + 32,
+  return launch_cluster_grid(c, KIND_FT, k_forward_tangent_rs<NE, NC, NT, L, GC, LA>, ncl * NC, NC, NT + 64,
                              rs_fw_smem<NT, L, GC, LA>(S), "k_forward_tangent_rs", M, (const unsigned char*)c->tape_rs_fw, K, Kp, S,
-                             c->pass_thi, (const double*)c->d_zero, dpol, pd_rs ? 1 : 0, dkdpart);
+                             c->pass_thi, (const double*)c->d_zero, dpol, pd_rs ? 1 : 0, dkdpart, c->rs_relaxed ? 0 : 1);
 }
 // clusters of this shape that can be resident at once (the smaller of the two sweeps' answers)
 template <int NE, int NC, int NT, int L, int GC, int LA>
@@ -88,7 +88,7 @@ static int rs_cap_shape(hank_ctx* c) {
   auto ask = [&](auto kern, size_t smem) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); cap = 0; return; }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(NC * 64); cfg.blockDim = dim3(NT + 32); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+    cfg.gridDim = dim3(NC * 64); cfg.blockDim = dim3(NT + 64); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = NC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;

@@ -60,13 +60,38 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// Both arrivals are RELAXED: with the default release semantics ptxas puts MEMBAR.ALL.CTA + ERRBAR in front of the
-// arrive, and the arriving threads have policy-tangent stores to HBM in flight, so every hand-shake waited for a DRAM
-// write round trip (19 % of the stall samples of the 2-lane shape, profiles/r02_notes.md).  What the arrivals publish
-// is shared memory written before the preceding bar.sync (which drains the stores) or a slot whose loads have
-// already been consumed; no global data is handed over through these barriers.
+// The remote arrival RELEASES at cluster scope: it publishes shared memory that other threads of the CTA wrote before the
+// named barrier in front of it, to readers in other CTAs.  A relaxed arrival here (round 2's first version) was a real
+// race: alone on the GPU it never showed in thousands of sweeps, but with the Jacobian build's overflow clusters
+// running next to the 148-CTA main wave one unit-seed column in ~15 builds came out 3e-7 .. 1e-4 off (a pulled value
+// read before the owner's store was visible to the cluster).  Measured remedies (profiles/r02_notes.md): a CTA-scope
+// fence before a relaxed arrival and a cluster-scope acquire on the reader's side both still fail; only the
+// cluster-scope release is clean (0 of 200 builds), and it costs ~0.45 us per hand-shake whoever issues it.
+// The arrivals are issued by a SIGNALLING WARP that owns no rows: the compute warps `bar.arrive` on a named barrier
+// after their shared-memory writes and go on to the work that does not depend on the peers; the signalling warp
+// `bar.sync`s on it and then releases.  The slot hand-back to the producer warp stays relaxed: the loads of that slot
+// have already been consumed.  (The fence-free way to publish would be to PUSH the values with st.async +
+// complete_tx into every reader's shared memory, as the primal sweeps do; that is the next step for these kernels.)
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+// (HANK_RS_RELAXED=1, A/B measurements only: the racy fast form)
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t remote_bar) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// the signalling warp's loop: one hand-shake per exchange group, buffers in ring order
+template <int NC, int NB>
+__device__ __forceinline__ void signal_groups(uint64_t* ready, int ngroups, int nthreads_bar, int lane, int release) {
+  const uint32_t rdy_remote = lane < NC ? map_to_cta(smem_u32(ready), (uint32_t)lane) : 0u;
+  int b = 0;
+  for (int q = 0; q < ngroups; ++q) {
+    asm volatile("bar.sync %0, %1;" ::"r"(1), "r"(nthreads_bar) : "memory");
+    if (lane < NC) { if (release) mbar_arrive_remote(rdy_remote + 8u * (uint32_t)b); else mbar_arrive_remote_relaxed(rdy_remote + 8u * (uint32_t)b); }
+    if (++b == NB) b = 0;
+  }
 }
 __device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
   asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -116,10 +141,10 @@ struct Cursor {
 // thi (nullable): seed horizons per kThiGroup lanes (hank_ks_jacobian_columns).
 // ======================================================================================
 template <int NE, int NC, int NT, int L, int GC, int LA>
-__global__ void __launch_bounds__(NT + 32, 1)
+__global__ void __launch_bounds__(NT + 64, 1)
 k_backward_tangent_rs(const Consts<NE> M, const Tape tp, const unsigned char* __restrict__ tape_rs, int K, int S,
                       const int* __restrict__ thi, const double* __restrict__ dr, const double* __restrict__ dw,
-                      double* __restrict__ dpol) {
+                      double* __restrict__ dpol, int release) {
   static_assert(GC >= 1 && GC <= NE, "columns per exchange group");   // the last group may be shorter
   static_assert(NT % 32 == 0 && (NT & (NT - 1)) == 0, "NT must be a power of two >= 32");
   constexpr int LDA = NC * NT, NG = (NE + GC - 1) / GC, NB = 2 * LA + 2, LOGNT = ilog2c(NT), NW = NT / 32;
@@ -164,6 +189,8 @@ k_backward_tangent_rs(const Consts<NE> M, const Tape tp, const unsigned char* __
         if (++g == NG) { g = 0; --t; }
       }
     }
+  } else if (warp == NW + 1) {
+    signal_groups<NC, NB>(ready, ngroups, NT + 32, lane, release);   // ---- signalling warp (see mbar_arrive_remote)
   } else {
     double Vd[L][NE];
 #pragma unroll
@@ -171,8 +198,6 @@ k_backward_tangent_rs(const Consts<NE> M, const Tape tp, const unsigned char* __
 #pragma unroll
       for (int e = 0; e < NE; ++e) Vd[l][e] = 0.0;
 
-    uint32_t rdy_remote = 0;   // this thread's target CTA's ready[0] (threads 0..NC-1 signal one CTA each)
-    if (tid < NC) rdy_remote = map_to_cta(smem_u32(ready), (uint32_t)tid);
     Cursor sA, sB, bA, bB;     // tape slot / exchange buffer of the next write (A) and read (B) stage
     double rho = __ldg(tp.rho + (P > 0 ? P - 1 : 0));
     double drn[L], dwn[L];
@@ -257,8 +282,10 @@ k_backward_tangent_rs(const Consts<NE> M, const Tape tp, const unsigned char* __
 #pragma unroll
             for (int l = 0; l < L; ++l) kw[(ce * L + l) * NT] = fma(a1, Vd[l][e], fma(kr, drl[l], cw * dwl[l]));
           }
-          named_bar_sync(1, NT);   // all k̇ of the group are in shared memory (BAR drains the stores)
-          if (tid < NC) mbar_arrive_remote(rdy_remote + 8u * bA.i);
+          // this thread's k̇ of the group are written: the signalling warp tells the peers.  Without look-ahead the next
+          // thing a thread does is wait for the peers' arrivals of this very group, so it need not wait here; with
+          // look-ahead it could reach the next group's barrier before this one completed, so it waits like everyone
+          if constexpr (LA == 0) named_bar_arrive(1, NT + 32); else named_bar_sync(1, NT + 32);
           sA.next(S); bA.next(NB);
         }
         if (LA == 0) B1();
@@ -359,10 +386,10 @@ __device__ __forceinline__ void gather_rs_rest(const double* xl, const double* y
 }
 
 template <int NE, int NC, int NT, int L, int GC, int LA>
-__global__ void __launch_bounds__(NT + 32, 1)
+__global__ void __launch_bounds__(NT + 64, 1)
 k_forward_tangent_rs(const Consts<NE> M, const unsigned char* __restrict__ tape_rs, int K, int Kp, int S,
                      const int* __restrict__ thi, const double* __restrict__ zeros, const double* __restrict__ dpol,
-                     int pd_rs, double* __restrict__ dkdpart) {
+                     int pd_rs, double* __restrict__ dkdpart, int release) {
   static_assert(GC >= 1 && GC <= NE, "columns per exchange group");   // the last group may be shorter
   constexpr int LDA = NC * NT, NG = (NE + GC - 1) / GC, NB = 2 * LA + 2, NW = NT / 32;
   constexpr int COLB = (int)rs_fw_tape_col_bytes<NT>(), COLD = COLB / 8;   // 36*NT + 16 bytes, a multiple of 16
@@ -426,14 +453,14 @@ k_forward_tangent_rs(const Consts<NE> M, const unsigned char* __restrict__ tape_
       cs.next(S);
       if (++g == NG) { g = 0; ++t; }
     }
+  } else if (warp == NW + 1) {
+    signal_groups<NC, NB>(ready, ngroups, NT + 32, lane, release);   // ---- signalling warp (see mbar_arrive_remote)
   } else {
     double Dd[L][NE];
 #pragma unroll
     for (int l = 0; l < L; ++l)
 #pragma unroll
       for (int e = 0; e < NE; ++e) Dd[l][e] = 0.0;
-    uint32_t rdy_remote = 0;
-    if (tid < NC) rdy_remote = map_to_cta(smem_u32(ready), (uint32_t)tid);
     Cursor sA, sB, bA, bB;
     for (int t = 0; t < P; ++t) {
       double kacc[L];
@@ -485,8 +512,9 @@ k_forward_tangent_rs(const Consts<NE> M, const unsigned char* __restrict__ tape_
               kacc[l] = fma(pd[l], Dn, kacc[l]);
             }
           }
-          named_bar_sync(1, NT);
-          if (tid < NC) mbar_arrive_remote(rdy_remote + 8u * bA.i);
+          // this thread's masses of the group are written: the signalling warp tells the peers (see the backward sweep)
+          if constexpr (LA == 0) named_bar_arrive(1, NT + 32); else named_bar_sync(1, NT + 32);
+          if (st == 0 && t > 0) named_bar_sync(3, NT);   // every warp's partial of the previous period is in `red`
           if (st == 0 && t > 0 && tid < L && lane0 + tid < K) {   // the previous period's K̇D share of this CTA
             double s = 0.0;
 #pragma unroll
@@ -542,7 +570,7 @@ k_forward_tangent_rs(const Consts<NE> M, const unsigned char* __restrict__ tape_
         if (lane == 0) red[((t & 1) * L + l) * NW + warp] = s;
       }
     }
-    named_bar_sync(1, NT);
+    named_bar_sync(3, NT);
     if (tid < L && lane0 + tid < K && P > 0) {
       double s = 0.0;
 #pragma unroll
@@ -561,7 +589,7 @@ k_forward_tangent_rs(const Consts<NE> M, const unsigned char* __restrict__ tape_
 // one per scheduler at 64 rows — and each of them walks all n_e columns of its rows: ~585 dependent-latency
 // instructions per warp and period (profiles/r02_notes.md: 4.2 M warp instructions for 299 periods on 8 CTAs, issue
 // slots 17 % busy), i.e. 1.84 us per period whatever the hardware could overlap.  Here the n_e columns of a row go to
-// n_e different warps (thread = (e, row), NE*NT threads + the producer warp), so a warp's chain per period is one
+// n_e different warps (thread = (e, row), NE*NT threads + the producer and the signalling warp), so a warp's chain per period is one
 // column (~70 instructions) and four to seven warps share a scheduler.  The price is the Markov mix: the post-lottery
 // masses of a row meet through shared memory (one more named barrier per period) and every thread forms the mixed
 // mass of its own income state.  Everything else — ring, producer warp, exchange buffers, hand-shake, DSMEM pulls,
@@ -575,10 +603,10 @@ constexpr size_t rs_fw_ce_smem(int S) {
          (size_t)(2 * S + 2) * 8 + 128;
 }
 template <int NE, int NC, int NT>
-__global__ void __launch_bounds__(NE * NT + 32, 1)
+__global__ void __launch_bounds__(NE * NT + 64, 1)
 k_forward_tangent_rs_ce(const Consts<NE> M, const unsigned char* __restrict__ tape_rs, int K, int Kp, int S,
                         const int* __restrict__ thi, const double* __restrict__ zeros, const double* __restrict__ dpol,
-                        int pd_rs, double* __restrict__ dkdpart) {
+                        int pd_rs, double* __restrict__ dkdpart, int release) {
   constexpr int LDA = NC * NT, NB = 2, NTC = NE * NT, NWC = NTC / 32;
   constexpr int COLB = (int)rs_fw_tape_col_bytes<NT>(), COLD = COLB / 8;
   constexpr int ST_OFF = FW_NF * NT, PD_OFF = NE * COLD, SLOTD = NE * COLD + NE * NT, XYD = NE * NT;
@@ -631,14 +659,14 @@ k_forward_tangent_rs_ce(const Consts<NE> M, const unsigned char* __restrict__ ta
           bulk_g2s(dst + PD_OFF + (size_t)i * NT, dpol + ((((size_t)t * NE + i) * Kp + lane0) * LDA + rank * NT), NT * 8, &full[cs.i]);
       cs.next(S);
     }
+  } else if (warp == NWC + 1) {
+    signal_groups<NC, NB>(ready, P, NTC + 32, lane, release);   // ---- signalling warp (see mbar_arrive_remote)
   } else {
     const int e = tid / NT, row = tid - e * NT;   // (warp-uniform e)
     double pic[NE];                               // Π[·, e]: this thread forms the mixed mass of income state e
 #pragma unroll
     for (int e1 = 0; e1 < NE; ++e1) pic[e1] = M.Pi[e1][e];
     double Dd = 0.0;
-    uint32_t rdy_remote = 0;
-    if (tid < NC) rdy_remote = map_to_cta(smem_u32(ready), (uint32_t)tid);
     Cursor sl_c, b_c;
     for (int t = 0; t < P; ++t) {
       // ---- A: lottery masses ẋ, ẏ of this (row, income state)
@@ -654,14 +682,7 @@ k_forward_tangent_rs_ce(const Consts<NE> M, const unsigned char* __restrict__ ta
       xw[e * NT + row] = xd;
       xw[XYD + e * NT + row] = Dd - xd;
       double kacc = pd * Dn;
-      named_bar_sync(1, NTC);
-      if (tid < NC) mbar_arrive_remote(rdy_remote + 8u * b_c.i);
-      if (t > 0 && tid == 0 && lane0 < K) {   // the previous period's K̇D share of this CTA
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < NWC; ++w) s += red[((t - 1) & 1) * NWC + w];
-        dkdpart[((size_t)lane0 * P + (t - 1)) * NC + rank] = s;
-      }
+      named_bar_arrive(1, NTC + 32);   // this thread's masses are written: the signalling warp tells the peers
       // ---- B: the sources of this destination row, pulled from their owners
       const double* xr_l = xw;
       const uint32_t xr_s = xy_s + (uint32_t)(b_c.i * 2 * XYD) * 8u;
@@ -685,6 +706,12 @@ k_forward_tangent_rs_ce(const Consts<NE> M, const unsigned char* __restrict__ ta
       // ---- Markov mix across the income states of the row (through shared memory) and <p_t, Ḋ_t>
       mix[e * NT + row] = acc[0];
       named_bar_sync(2, NTC);
+      if (t > 0 && tid == 0 && lane0 < K) {   // the previous period's K̇D share of this CTA (every warp wrote its
+        double s = 0.0;                       // partial before it reached this barrier)
+#pragma unroll
+        for (int w = 0; w < NWC; ++w) s += red[((t - 1) & 1) * NWC + w];
+        dkdpart[((size_t)lane0 * P + (t - 1)) * NC + rank] = s;
+      }
       double d = 0.0;
 #pragma unroll
       for (int e1 = 0; e1 < NE; ++e1) d = fma(pic[e1], mix[e1 * NT + row], d);
@@ -694,7 +721,7 @@ k_forward_tangent_rs_ce(const Consts<NE> M, const unsigned char* __restrict__ ta
       if (lane == 0) red[(t & 1) * NWC + warp] = s;
       sl_c.next(S); b_c.next(NB);
     }
-    named_bar_sync(1, NTC);
+    named_bar_sync(3, NTC);
     if (tid == 0 && lane0 < K && P > 0) {
       double s = 0.0;
 #pragma unroll
