@@ -199,7 +199,9 @@ static bool rowsplit_cfg(const hank_ctx* c, int K, TangentCfg* out) {
   const int nc = c->lda == 256 ? 4 : 8, nt = c->lda / nc;
   // a whole period per exchange when the period's tape rows fit the ring twice over, else column by column
   const bool whole = (size_t)2 * ne * (52 * nt) + (size_t)2 * ne * nt * 8 + 1024 <= (size_t)c->smem_max && c->lda <= 1024;
-  const TangentCfg one = whole ? TangentCfg{nt, 1, 1, nc, ne, 0} : TangentCfg{nt, 1, 1, nc, 1, 2};
+  // (otherwise four columns per exchange: with the cluster-scope release a hand-shake costs ~0.45 us, so few large groups
+  // beat the column-by-column look-ahead pipeline that the relaxed hand-shakes favoured)
+  const TangentCfg one = whole ? TangentCfg{nt, 1, 1, nc, ne, 0} : TangentCfg{nt, 1, 1, nc, 4, 0};
   hank_ctx* cm = const_cast<hank_ctx*>(c);
   if (c->rs_cap[0] < 0) cm->rs_cap[0] = Sweeps<NE>::rs_max_clusters(cm, one.NC, one.NT, one.L, one.GC);
   const int max_k = c->rs_max_k > 0 ? c->rs_max_k : c->rs_cap[0];

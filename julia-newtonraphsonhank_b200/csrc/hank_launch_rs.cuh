@@ -110,7 +110,7 @@ static int rs_cap_shape(hank_ctx* c) {
     if (g.NC == 4 && g.NT == 64 && g.L == 1 && g.GC == NE) return FN<NE, 4, 64, 1, NE, 0>(__VA_ARGS__);   \
     if (g.NC == 8 && g.NT == 64 && g.L == 1 && g.GC == NE) return FN<NE, 8, 64, 1, NE, 0>(__VA_ARGS__);   \
     if (g.NC == 8 && g.NT == 128 && g.L == 1 && g.GC == NE) return FN<NE, 8, 128, 1, NE, 0>(__VA_ARGS__); \
-    if (g.NC == 8 && g.NT == 256 && g.L == 1 && g.GC == 1) return FN<NE, 8, 256, 1, 1, 2>(__VA_ARGS__);   \
+    if (g.NC == 8 && g.NT == 256 && g.L == 1 && g.GC == 4) return FN<NE, 8, 256, 1, (NE < 4 ? NE : 4), 0>(__VA_ARGS__); \
     if (g.NC == 2 && g.NT == 256 && g.L == 1 && g.GC == NE) return FN<NE, 2, 256, 1, NE, 0>(__VA_ARGS__);  \
     if (g.NC == 4 && g.NT == 256 && g.L == 2 && g.GC == 4) return FN<NE, 4, 256, 2, (NE < 4 ? NE : 4), 0>(__VA_ARGS__); \
     if (g.NC == 4 && g.NT == 512 && g.L == 2 && g.GC == 2) return FN<NE, 4, 512, 2, 2, 0>(__VA_ARGS__);   \
