@@ -15,25 +15,34 @@ static int rs_ring_slots(const hank_ctx* c, size_t fixed, size_t slot, int min_s
 }
 // Row-block-major copies of the tape (k_tape_rowblocks_*), made on first use per linearisation and block size NT
 // (a K = 1 pass after a K = 64 pass at the same linearisation uses another cluster shape, hence another layout).
+static size_t tape_rs_rng_offset(const hank_ctx* c, bool forward) {
+  const size_t ncols = (size_t)c->P_alloc * c->n_e;
+  return forward ? ncols * (36 * (size_t)c->lda + 16 * (size_t)(c->lda / 32)) : ncols * 52 * (size_t)c->lda;
+}
 static int ensure_tape_rs(hank_ctx* c, int P, int NT, bool forward) {
   const size_t ncols = (size_t)c->P_alloc * c->n_e;
   // (sized for the smallest block any shape uses, 32 rows: the forward copy carries 4 extra range starts per block)
   const size_t bwb = ncols * 52 * (size_t)c->lda, fwb = ncols * (36 * (size_t)c->lda + 16 * (size_t)(c->lda / 32));
+  const size_t rngb = (size_t)c->P_alloc * 64 * sizeof(int);   // source-block ranges per (period, block) behind each copy
   if (!c->tape_rs_bw) {
-    int rc = cuda_check(c, cudaMalloc((void**)&c->tape_rs_bw, bwb), "cudaMalloc(tape_rs_bw)");
+    int rc = cuda_check(c, cudaMalloc((void**)&c->tape_rs_bw, bwb + rngb), "cudaMalloc(tape_rs_bw)");
     if (rc) return rc;
-    rc = cuda_check(c, cudaMalloc((void**)&c->tape_rs_fw, fwb), "cudaMalloc(tape_rs_fw)");
+    rc = cuda_check(c, cudaMalloc((void**)&c->tape_rs_fw, fwb + rngb), "cudaMalloc(tape_rs_fw)");
     if (rc) return rc;
   }
+  const int NCb = c->lda / NT;
+  const unsigned rgrid = (unsigned)(((size_t)P * NCb * 32 + 255) / 256);
   const size_t n = (size_t)P * c->n_e * c->lda;
   const unsigned grid = (unsigned)((n + 255) / 256);
   if (!forward && c->tape_rs_bw_nt != NT) {
     k_tape_rowblocks_bw<<<grid, 256, 0, c->stream>>>(c->tape.bw, c->tape_rs_bw, P * c->n_e, c->n_e, c->lda, NT);
-    c->launches++; c->tape_rs_bw_nt = NT;
+    k_rs_ranges<<<rgrid, 256, 0, c->stream>>>(c->tape_rs_bw, P, c->n_e, NCb, NT, c->n_a, 0, reinterpret_cast<int*>(c->tape_rs_bw + bwb));
+    c->launches += 2; c->tape_rs_bw_nt = NT;
   }
   if (forward && c->tape_rs_fw_nt != NT) {
     k_tape_rowblocks_fw<<<grid, 256, 0, c->stream>>>(c->tape.fw, c->tape_rs_fw, P * c->n_e, c->n_e, c->lda, NT);
-    c->launches++; c->tape_rs_fw_nt = NT;
+    k_rs_ranges<<<rgrid, 256, 0, c->stream>>>(c->tape_rs_fw, P, c->n_e, NCb, NT, c->n_a, 1, reinterpret_cast<int*>(c->tape_rs_fw + fwb));
+    c->launches += 2; c->tape_rs_fw_nt = NT;
   }
   return cuda_check(c, cudaGetLastError(), "k_tape_rowblocks");
 }
@@ -44,6 +53,19 @@ static int bt_rs_launch(hank_ctx* c, int P, int K, const double* dr, const doubl
   c->Kp_last = ncl * L;
   c->dpol_rs = true; c->dpol_rs_L = L; c->dpol_rs_NC = NC; c->dpol_rs_ncl = ncl;
   const size_t slot = (size_t)GC * rs_bw_col_bytes<NT>();
+  // one lane, a whole period per exchange: the push kernels (hank_tangent_rowsplit.cuh) where their buffers fit
+  if constexpr (L == 1 && GC == NE && LA == 0 && NE * NT + 64 <= 1024) {
+    static const bool no_push = getenv("HANK_NO_RS_PUSH") != nullptr;
+    const int Sp = rs_ring_slots(c, rs_bw_push_smem<NE, NC, NT>(0), slot + 16, 2, 6);
+    if (!no_push && Sp >= 2) {
+      int rc = ensure_tape_rs(c, P, NT, false);
+      if (rc) return rc;
+      rc = launch_cluster_grid(c, KIND_BT, k_backward_tangent_rs_push<NE, NC, NT>, ncl * NC, NC, NE * NT + 64, rs_bw_push_smem<NE, NC, NT>(Sp),
+                               "k_backward_tangent_rs_push", M, c->tape, (const unsigned char*)c->tape_rs_bw,
+                               reinterpret_cast<const int*>(c->tape_rs_bw + tape_rs_rng_offset(c, false)), K, Sp, c->pass_thi, dr, dw, dpol);
+      if (rc >= 0) return rc;
+    }
+  }
   const int S = rs_ring_slots(c, rs_bw_smem<NT, L, GC, LA>(0), slot + 16, LA + 2, GC == 1 ? 3 * NE : 6);
   if (S < LA + 2) return -1;
   int rc = ensure_tape_rs(c, P, NT, false);
@@ -62,6 +84,17 @@ static int ft_rs_launch(hank_ctx* c, int P, int K, const double* dpol, double* d
   const size_t slot = (size_t)GC * rs_fw_col_bytes<NT, L>();
   // one lane, a whole period per exchange: a thread per (income state, row) instead of per row (hank_tangent_rowsplit.cuh)
   if constexpr (L == 1 && GC == NE && LA == 0 && NE * NT + 64 <= 1024) {
+    static const bool no_push = getenv("HANK_NO_RS_PUSH") != nullptr;
+    const int Sp = rs_ring_slots(c, rs_fw_push_smem<NE, NC, NT>(0), slot + 16, 2, 6);
+    if (!no_push && Sp >= 2) {
+      int rc = ensure_tape_rs(c, P, NT, true);
+      if (rc) return rc;
+      rc = launch_cluster_grid(c, KIND_FT, k_forward_tangent_rs_push<NE, NC, NT>, ncl * NC, NC, NE * NT + 64, rs_fw_push_smem<NE, NC, NT>(Sp),
+                               "k_forward_tangent_rs_push", M, (const unsigned char*)c->tape_rs_fw,
+                               reinterpret_cast<const int*>(c->tape_rs_fw + tape_rs_rng_offset(c, true)), K, Kp, Sp, c->pass_thi,
+                               (const double*)c->d_zero, dpol, pd_rs ? 1 : 0, dkdpart);
+      if (rc >= 0) return rc;
+    }
     static const bool no_ce = getenv("HANK_NO_RS_CE") != nullptr;
     const int Sc = rs_ring_slots(c, rs_fw_ce_smem<NE, NT>(0), slot + 16, 2, 6);
     if (!no_ce && Sc >= 2) {

@@ -734,6 +734,343 @@ k_forward_tangent_rs_ce(const Consts<NE> M, const unsigned char* __restrict__ ta
 }
 
 // ======================================================================================
+// One-lane sweeps that PUSH instead of pull (k_backward_tangent_rs_push, k_forward_tangent_rs_push).
+//
+// The pull kernels above publish generic-proxy shared-memory writes to the cluster, which needs a cluster-scope
+// release (~0.45 us per hand-shake) on top of the remote-load round trips.  Here an owner's block of exchanged values
+// travels through the ASYNC proxy instead, the way TMA stores leave shared memory: the compute threads write their
+// values to a local staging block and execute fence.proxy.async, a named barrier hands the block to a pushing warp,
+// and that warp copies it with ONE cp.async.bulk.shared::cluster per destination CTA into the destination's
+// full-width buffer, completing bytes on the destination's mbarrier (complete_tx).  Readers wait on their own
+// mbarrier — the sanctioned completion mechanism for async-proxy writes, no fence — and then gather from LOCAL
+// shared memory.  Only the CTAs that need a block get it: the range of source blocks a destination block reads in a
+// period (lottery source ranges / interpolation knots, both known from the primal tape) is tabulated per
+// (period, destination) by k_rs_ranges; everybody else receives a 16-byte token, so that every CTA still hears from
+// every CTA once per period — that all-to-all is what makes the two-deep buffers safe (a CTA can only be one period
+// ahead of any other).  Thread = (income state, row) as in k_forward_tangent_rs_ce; one lane per cluster, a whole
+// period per exchange.
+// ======================================================================================
+__device__ __forceinline__ void bulk_s2c(uint32_t dst_cluster, const void* src, uint32_t bytes, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
+               "r"(smem_u32(src)), "r"(bytes), "r"(bar_cluster)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// range of source blocks each destination block reads, per period: out[t*NC + d] = lo | hi << 8 (lo > hi: none)
+// forward: sources of the lottery ranges [s0, s2) of the block's rows; backward: the knots i, i+1 of its rows
+static __global__ void k_rs_ranges(const unsigned char* __restrict__ tape_rs, int P, int NE, int NC, int NT, int n_a,
+                                   int forward, int* __restrict__ out) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= P * NC) return;
+  const int t = w / NC, d = w - t * NC;
+  int lognt = 0;
+  while ((1 << lognt) < NT) ++lognt;
+  const size_t colb = forward ? (size_t)FW_NF * NT * 8 + (size_t)(NT + 4) * 4 : (size_t)BW_NF * NT * 8 + (size_t)NT * 4;
+  const size_t into = forward ? (size_t)FW_NF * NT * 8 : (size_t)BW_NF * NT * 8;
+  int lo = NC, hi = -1;
+  for (int e = 0; e < NE; ++e) {
+    const int* ints = reinterpret_cast<const int*>(tape_rs + (((size_t)t * NC + d) * NE + e) * colb + into);
+    for (int r = lane; r < NT; r += 32) {
+      if (d * NT + r >= n_a) continue;
+      if (forward) {
+        const int s0 = ints[r + 1], s2 = ints[r + 3];
+        if (s2 > s0) { lo = min(lo, s0 >> lognt); hi = max(hi, (s2 - 1) >> lognt); }
+      } else {
+        const int i0 = ints[r];
+        lo = min(lo, i0 >> lognt); hi = max(hi, (i0 + 1) >> lognt);
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+  if (lane == 0) { lo = max(lo, 0); hi = min(hi, NC - 1); out[w] = lo > hi ? 1 : (lo | (hi << 8)); }
+}
+__device__ __forceinline__ bool rng_has(int rng, int s) { return (rng & 255) <= s && s <= ((rng >> 8) & 255); }
+__device__ __forceinline__ int rng_count(int rng) { const int lo = rng & 255, hi = (rng >> 8) & 255; return hi >= lo ? hi - lo + 1 : 0; }
+
+// the pushing warp's loop: per period, arm this CTA's barrier with what it will receive, wait for the local block,
+// send it (or a token) to every CTA.  BLKB: bytes of a block.  tok: [2][NC] 16-byte slots.
+template <int NC>
+__device__ __forceinline__ void push_periods(const int* __restrict__ rng, int t_first, int t_step, int P, uint32_t rank,
+                                             const double* stg, int stg_stride_d, double* full_buf, int full_stride_d, int blkd,
+                                             uint32_t blkb, double* tok, uint64_t* xbar, int nthreads_bar, int lane) {
+  const uint32_t full_s = smem_u32(full_buf), tok_s = smem_u32(tok), bar_s = smem_u32(xbar);
+  int t = t_first;
+  for (int it = 0; it < P; ++it, t += t_step) {
+    const int b = it & 1;
+    const int mine = __ldg(rng + (size_t)t * NC + rank);            // what this CTA receives this period
+    const int theirs = lane < NC ? __ldg(rng + (size_t)t * NC + lane) : 1;
+    if (lane == 0) mbar_expect_tx(&xbar[b], (uint32_t)rng_count(mine) * blkb + (uint32_t)(NC - rng_count(mine)) * 16u);
+    asm volatile("bar.sync %0, %1;" ::"r"(1), "r"(nthreads_bar) : "memory");   // the block is staged (and proxy-fenced)
+    if (lane < NC) {
+      const uint32_t bar_r = map_to_cta(bar_s + 8u * (uint32_t)b, (uint32_t)lane);
+      if (rng_has(theirs, (int)rank))
+        bulk_s2c(map_to_cta(full_s + (uint32_t)(b * full_stride_d + (int)rank * blkd) * 8u, (uint32_t)lane), stg + (size_t)b * stg_stride_d, blkb, bar_r);
+      else
+        bulk_s2c(map_to_cta(tok_s + (uint32_t)((b * NC + (int)rank) * 2) * 8u, (uint32_t)lane), tok + (size_t)(2 * NC) * 2, 16u, bar_r);
+    }
+  }
+}
+
+template <int NE, int NT> constexpr size_t rs_push_ring_slot_fw() { return (size_t)NE * rs_fw_col_bytes<NT, 1>(); }
+template <int NE, int NC, int NT>
+constexpr size_t rs_fw_push_smem(int S) {   // ring | stg[2][2 NE NT] | full[2][NC][2 NE NT] | mix[NE NT] | red | tok[(2 NC + 1) x 16 B] | barriers
+  return (size_t)S * rs_push_ring_slot_fw<NE, NT>() + (size_t)2 * 2 * NE * NT * 8 + (size_t)2 * NC * 2 * NE * NT * 8 + (size_t)NE * NT * 8 +
+         (size_t)2 * (NE * NT / 32) * 8 + (size_t)(2 * NC + 1) * 16 + (size_t)(2 * S + 2) * 8 + 128;
+}
+template <int NE, int NC, int NT>
+__global__ void __launch_bounds__(NE * NT + 64, 1)
+k_forward_tangent_rs_push(const Consts<NE> M, const unsigned char* __restrict__ tape_rs, const int* __restrict__ rng, int K, int Kp,
+                          int S, const int* __restrict__ thi, const double* __restrict__ zeros, const double* __restrict__ dpol,
+                          int pd_rs, double* __restrict__ dkdpart) {
+  constexpr int LDA = NC * NT, NTC = NE * NT, NWC = NTC / 32, LOGNT = ilog2c(NT);
+  constexpr int COLB = (int)rs_fw_tape_col_bytes<NT>(), COLD = COLB / 8;
+  constexpr int ST_OFF = FW_NF * NT, PD_OFF = NE * COLD, SLOTD = NE * COLD + NE * NT;
+  constexpr int BLKD = 2 * NE * NT;                 // a block: x[NE][NT] | y[NE][NT]
+  static_assert(NT % 32 == 0 && NC <= 32, "shape");
+  extern __shared__ __align__(128) unsigned char smem_rs[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_rank();
+  const int cluster = blockIdx.x / NC, ncl = gridDim.x / NC;
+  const int lane0 = cluster;
+  const int P = M.P, n_a = M.n_a;
+  double* ring = reinterpret_cast<double*>(smem_rs);
+  double* stg = ring + (size_t)S * SLOTD;
+  double* fullb = stg + 2 * BLKD;
+  double* mix = fullb + (size_t)2 * NC * BLKD;
+  double* red = mix + NTC;
+  double* tok = red + 2 * NWC;                      // [2][NC] receive slots + one send slot, 16 bytes each
+  uint64_t* full = reinterpret_cast<uint64_t*>(tok + (2 * NC + 1) * 2);
+  uint64_t* empty = full + S;
+  uint64_t* xbar = empty + S;
+  const int pe = thi ? min(P, thi[lane0 / kThiGroup]) : P;
+  (void)n_a;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWC); }
+    mbar_init(&xbar[0], 1); mbar_init(&xbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (tid < (2 * NC + 1) * 2) tok[tid] = 0.0;
+  __syncthreads();
+  cluster_sync_all();
+
+  if (warp == NWC) {
+    // ---- producer warp (as in k_forward_tangent_rs_ce)
+    Cursor cs;
+    for (int t = 0; t < P; ++t) {
+      double* dst = ring + (size_t)cs.i * SLOTD;
+      constexpr uint32_t PDB = (uint32_t)(NE * NT * 8);
+      if (lane == 0) {
+        if (t >= S) mbar_wait(&empty[cs.i], cs.par ^ 1);
+        mbar_expect_tx(&full[cs.i], (uint32_t)(NE * COLB) + PDB);
+        bulk_g2s(dst, tape_rs + (((size_t)t * NC + rank) * NE) * COLB, (uint32_t)(NE * COLB), &full[cs.i]);
+        if (t >= pe) {
+          for (uint32_t o = 0; o < PDB; o += kZeroBytes)
+            bulk_g2s(dst + PD_OFF + o / 8, zeros, min(PDB - o, (uint32_t)kZeroBytes), &full[cs.i]);
+        } else if (pd_rs) {
+          bulk_g2s(dst + PD_OFF, dpol + ((((size_t)t * ncl + cluster) * NC + rank) * NE) * NT, PDB, &full[cs.i]);
+        }
+      }
+      __syncwarp();
+      if (t < pe && !pd_rs)
+        for (int i = lane; i < NE; i += 32)
+          bulk_g2s(dst + PD_OFF + (size_t)i * NT, dpol + ((((size_t)t * NE + i) * Kp + lane0) * LDA + rank * NT), NT * 8, &full[cs.i]);
+      cs.next(S);
+    }
+  } else if (warp == NWC + 1) {
+    push_periods<NC>(rng, 0, 1, P, rank, stg, BLKD, fullb, NC * BLKD, BLKD, (uint32_t)BLKD * 8u, tok, xbar, NTC + 32, lane);
+  } else {
+    const int e = tid / NT, row = tid - e * NT;
+    double pic[NE];
+#pragma unroll
+    for (int e1 = 0; e1 < NE; ++e1) pic[e1] = M.Pi[e1][e];
+    double Dd = 0.0;
+    Cursor sl_c;
+    for (int t = 0; t < P; ++t) {
+      const int b = t & 1;
+      const double* sl = ring + (size_t)sl_c.i * SLOTD;
+      mbar_wait(&full[sl_c.i], sl_c.par);
+      const double pd = sl[PD_OFF + e * NT + row];
+      const double om = sl[e * COLD + FW_OM * NT + row], dco = sl[e * COLD + FW_DCO * NT + row];
+      const double Dn = sl[e * COLD + FW_D * NT + row], pv = sl[e * COLD + FW_P * NT + row];
+      const int* sst = reinterpret_cast<const int*>(sl + e * COLD + ST_OFF) + row + 1;
+      const int s0 = sst[0], s1 = sst[1], s2 = sst[2];
+      __syncwarp();
+      if (lane == 0) mbar_arrive_local(&empty[sl_c.i]);   // everything this warp needs of the slot is in registers
+      const double xd = fma(om, Dd, dco * pd);
+      stg[b * BLKD + e * NT + row] = xd;
+      stg[b * BLKD + NTC + e * NT + row] = Dd - xd;
+      double kacc = pd * Dn;
+      fence_proxy_async_smem();                 // this thread's staged values, before the pushing warp's bulk copies read them
+      named_bar_arrive(1, NTC + 32);
+      // ---- the sources of this destination row, from the blocks the peers pushed into this CTA
+      mbar_wait_cluster(&xbar[b], (uint32_t)((t >> 1) & 1));
+      const double* fb = fullb + (size_t)b * NC * BLKD + e * NT;
+      auto X = [&](int src) { return fb[(src >> LOGNT) * BLKD + (src & (NT - 1))]; };
+      auto Y = [&](int src) { return fb[(src >> LOGNT) * BLKD + NTC + (src & (NT - 1))]; };
+      const int n1 = s1 - s0, n2 = s2 - s1;
+      double acc = 0.0;                         // 0 + x0 + y0 + x1 + y1 + the rest of x, then of y: gather_row's order
+      if (n1 > 0) acc = X(s0);
+      if (n2 > 0) acc += Y(s1);
+      if (n1 > 1) acc += X(s0 + 1);
+      if (n2 > 1) acc += Y(s1 + 1);
+      const int mx = max(n1, n2) - 2;
+      if (__any_sync(0xffffffffu, mx > 0)) {
+        constexpr int kSerial = 8;
+        if (mx > 0 && mx <= kSerial) {
+          for (int q = s0 + 2; q < s1; ++q) acc += X(q);
+          for (int q = s1 + 2; q < s2; ++q) acc += Y(q);
+        }
+        unsigned bal = __ballot_sync(0xffffffffu, mx > kSerial);
+        while (bal) {                            // long ranges (the mass at the borrowing constraint): the whole warp
+          const int src = __ffs(bal) - 1;
+          bal &= bal - 1;
+          const int b0 = __shfl_sync(0xffffffffu, s0, src), b1 = __shfl_sync(0xffffffffu, s1, src), b2 = __shfl_sync(0xffffffffu, s2, src);
+          double v = 0.0;
+          for (int q = b0 + 2 + lane; q < b1; q += 32) v += X(q);
+          for (int q = b1 + 2 + lane; q < b2; q += 32) v += Y(q);
+          v = warp_sum(v);
+          if (lane == src) acc += v;
+        }
+      }
+      // ---- Markov mix across the income states of the row and <p_t, Ḋ_t>
+      mix[e * NT + row] = acc;
+      named_bar_sync(2, NTC);
+      if (t > 0 && tid == 0 && lane0 < K) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NWC; ++w) s += red[((t - 1) & 1) * NWC + w];
+        dkdpart[((size_t)lane0 * P + (t - 1)) * NC + rank] = s;
+      }
+      double d = 0.0;
+#pragma unroll
+      for (int e1 = 0; e1 < NE; ++e1) d = fma(pic[e1], mix[e1 * NT + row], d);
+      Dd = d;
+      kacc = fma(pv, d, kacc);
+      const double s = warp_sum(kacc);
+      if (lane == 0) red[(t & 1) * NWC + warp] = s;
+      sl_c.next(S);
+    }
+    named_bar_sync(3, NTC);
+    if (tid == 0 && lane0 < K && P > 0) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < NWC; ++w) s += red[((P - 1) & 1) * NWC + w];
+      dkdpart[((size_t)lane0 * P + (P - 1)) * NC + rank] = s;
+    }
+  }
+  __syncwarp();
+  cluster_sync_all();
+}
+
+template <int NE, int NC, int NT>
+constexpr size_t rs_bw_push_smem(int S) {   // ring | stg[2][NE NT] | full[2][NC][NE NT] | mixv[NE NT] | tok | barriers
+  return (size_t)S * NE * rs_bw_col_bytes<NT>() + (size_t)2 * NE * NT * 8 + (size_t)2 * NC * NE * NT * 8 + (size_t)NE * NT * 8 +
+         (size_t)(2 * NC + 1) * 16 + (size_t)(2 * S + 2) * 8 + 128;
+}
+template <int NE, int NC, int NT>
+__global__ void __launch_bounds__(NE * NT + 64, 1)
+k_backward_tangent_rs_push(const Consts<NE> M, const Tape tp, const unsigned char* __restrict__ tape_rs, const int* __restrict__ rng,
+                           int K, int S, const int* __restrict__ thi, const double* __restrict__ dr, const double* __restrict__ dw,
+                           double* __restrict__ dpol) {
+  constexpr int NTC = NE * NT, NWC = NTC / 32, LOGNT = ilog2c(NT);
+  constexpr int COLB = (int)rs_bw_col_bytes<NT>(), COLD = COLB / 8, SLOTD = NE * COLD;
+  constexpr int BLKD = NE * NT;                     // a block: k̇[NE][NT]
+  static_assert(NT % 32 == 0 && NC <= 32, "shape");
+  extern __shared__ __align__(128) unsigned char smem_rs[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_rank();
+  const int cluster = blockIdx.x / NC, ncl = gridDim.x / NC;
+  const int lane0 = cluster;
+  const int Pfull = M.P, P = thi ? min(M.P, thi[lane0 / kThiGroup]) : M.P, n_a = M.n_a;
+  double* ring = reinterpret_cast<double*>(smem_rs);
+  double* stg = ring + (size_t)S * SLOTD;
+  double* fullb = stg + 2 * BLKD;
+  double* mixv = fullb + (size_t)2 * NC * BLKD;
+  double* tok = mixv + NTC;
+  uint64_t* full = reinterpret_cast<uint64_t*>(tok + (2 * NC + 1) * 2);
+  uint64_t* empty = full + S;
+  uint64_t* xbar = empty + S;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWC); }
+    mbar_init(&xbar[0], 1); mbar_init(&xbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (tid < (2 * NC + 1) * 2) tok[tid] = 0.0;
+  __syncthreads();
+  cluster_sync_all();
+
+  if (warp == NWC) {
+    if (lane == 0) {   // ---- producer: this CTA's rows of the period's tape, one piece
+      Cursor cs;
+      for (int it = 0; it < P; ++it) {
+        const int t = P - 1 - it;
+        if (it >= S) mbar_wait(&empty[cs.i], cs.par ^ 1);
+        mbar_expect_tx(&full[cs.i], (uint32_t)(NE * COLB));
+        bulk_g2s(ring + (size_t)cs.i * SLOTD, tape_rs + (((size_t)t * NC + rank) * NE) * COLB, (uint32_t)(NE * COLB), &full[cs.i]);
+        cs.next(S);
+      }
+    }
+  } else if (warp == NWC + 1) {
+    push_periods<NC>(rng, P - 1, -1, P, rank, stg, BLKD, fullb, NC * BLKD, BLKD, (uint32_t)BLKD * 8u, tok, xbar, NTC + 32, lane);
+  } else {
+    const int e = tid / NT, row = tid - e * NT;
+    const bool live = (int)rank * NT + row < n_a;
+    double pir[NE];                                   // Π[e, ·]
+#pragma unroll
+    for (int e2 = 0; e2 < NE; ++e2) pir[e2] = M.Pi[e][e2];
+    const double ze = M.z[e];
+    const bool on = lane0 < K && P > 0;
+    double Vd = 0.0;
+    double rho = __ldg(tp.rho + (P > 0 ? P - 1 : 0));
+    double drn = on ? __ldg(dr + (size_t)lane0 * Pfull + P - 1) : 0.0, dwn = on ? __ldg(dw + (size_t)lane0 * Pfull + P - 1) : 0.0;
+    Cursor sl_c;
+    for (int it = 0; it < P; ++it) {
+      const int t = P - 1 - it, b = it & 1;
+      const double rho_t = rho, drl = drn, dwl = dwn;
+      if (t > 0) {
+        rho = __ldg(tp.rho + t - 1);
+        drn = on ? __ldg(dr + (size_t)lane0 * Pfull + t - 1) : 0.0;
+        dwn = on ? __ldg(dw + (size_t)lane0 * Pfull + t - 1) : 0.0;
+      }
+      // ---- ĖV of this income state: the row's V̇ of all income states meet in shared memory
+      mixv[e * NT + row] = Vd;
+      named_bar_sync(3, NTC);
+      double ev = 0.0;
+#pragma unroll
+      for (int e2 = 0; e2 < NE; ++e2) ev = fma(pir[e2], mixv[e2 * NT + row], ev);
+      // ---- k̇ of this (row, income state), staged for the pushing warp
+      const double* sl = ring + (size_t)sl_c.i * SLOTD + e * COLD + row;
+      mbar_wait(&full[sl_c.i], sl_c.par);
+      const double a1 = sl[BW_A1 * NT], kr = sl[BW_KR * NT];
+      const double cA = sl[BW_CA * NT], cB = sl[BW_CB * NT], E1 = sl[BW_E1 * NT], vf = sl[BW_VF * NT];
+      const int i0 = reinterpret_cast<const int*>(sl - row + BW_NF * NT)[row];
+      __syncwarp();
+      if (lane == 0) mbar_arrive_local(&empty[sl_c.i]);
+      stg[b * BLKD + e * NT + row] = fma(a1, ev, fma(kr, drl, -(rho_t * ze) * dwl));
+      fence_proxy_async_smem();
+      named_bar_arrive(1, NTC + 32);
+      // ---- ṗ and V̇ from k̇ at the two knots (pushed into this CTA by their owners)
+      mbar_wait_cluster(&xbar[b], (uint32_t)((it >> 1) & 1));
+      const double* fb = fullb + (size_t)b * NC * BLKD + e * NT;
+      const int i1 = i0 + 1;
+      const double k0 = live ? fb[(i0 >> LOGNT) * BLKD + (i0 & (NT - 1))] : 0.0;
+      const double k1 = live ? fb[(i1 >> LOGNT) * BLKD + (i1 & (NT - 1))] : 0.0;
+      const double pd = fma(cA, k0, cB * k1);
+      __stcs(dpol + (((size_t)t * ncl + cluster) * NC + rank) * (size_t)(NE * NT) + e * NT + row, pd);
+      Vd = fma(vf, fma(ze, dwl, -pd), E1 * drl);
+      sl_c.next(S);
+    }
+  }
+  __syncwarp();
+  cluster_sync_all();
+}
+
+// ======================================================================================
 // Row-block-major copies of the primal tape for the kernels above (see the header comment).
 // One thread per (column, row): the row's coefficients and index / range start.
 // ======================================================================================
