@@ -19,30 +19,55 @@ static size_t tape_rs_rng_offset(const hank_ctx* c, bool forward) {
   const size_t ncols = (size_t)c->P_alloc * c->n_e;
   return forward ? ncols * (36 * (size_t)c->lda + 16 * (size_t)(c->lda / 32)) : ncols * 52 * (size_t)c->lda;
 }
+// behind the ranges: destinations per source (k_rs_st_mark_*, one int per grid point and period), then values received
+// per (period, CTA)
+static size_t tape_rs_info_offset(const hank_ctx* c, bool forward) { return tape_rs_rng_offset(c, forward) + (size_t)c->P_alloc * 64 * sizeof(int); }
+static size_t tape_rs_cnt_offset(const hank_ctx* c, bool forward) {
+  return tape_rs_info_offset(c, forward) + (size_t)c->P_alloc * c->n_e * c->lda * sizeof(int);
+}
 static int ensure_tape_rs(hank_ctx* c, int P, int NT, bool forward) {
   const size_t ncols = (size_t)c->P_alloc * c->n_e;
   // (sized for the smallest block any shape uses, 32 rows: the forward copy carries 4 extra range starts per block)
   const size_t bwb = ncols * 52 * (size_t)c->lda, fwb = ncols * (36 * (size_t)c->lda + 16 * (size_t)(c->lda / 32));
   const size_t rngb = (size_t)c->P_alloc * 64 * sizeof(int);   // source-block ranges per (period, block) behind each copy
+  const size_t infob = ncols * (size_t)c->lda * sizeof(int), cntb = rngb;
   if (!c->tape_rs_bw) {
-    int rc = cuda_check(c, cudaMalloc((void**)&c->tape_rs_bw, bwb + rngb), "cudaMalloc(tape_rs_bw)");
+    int rc = cuda_check(c, cudaMalloc((void**)&c->tape_rs_bw, bwb + rngb + infob + cntb), "cudaMalloc(tape_rs_bw)");
     if (rc) return rc;
-    rc = cuda_check(c, cudaMalloc((void**)&c->tape_rs_fw, fwb + rngb), "cudaMalloc(tape_rs_fw)");
+    rc = cuda_check(c, cudaMalloc((void**)&c->tape_rs_fw, fwb + rngb + infob + cntb), "cudaMalloc(tape_rs_fw)");
     if (rc) return rc;
   }
   const int NCb = c->lda / NT;
   const unsigned rgrid = (unsigned)(((size_t)P * NCb * 32 + 255) / 256);
   const size_t n = (size_t)P * c->n_e * c->lda;
   const unsigned grid = (unsigned)((n + 255) / 256);
+  const bool st = NT == 64 && NCb <= 8;   // the shapes of the st.async kernels
   if (!forward && c->tape_rs_bw_nt != NT) {
     k_tape_rowblocks_bw<<<grid, 256, 0, c->stream>>>(c->tape.bw, c->tape_rs_bw, P * c->n_e, c->n_e, c->lda, NT);
     k_rs_ranges<<<rgrid, 256, 0, c->stream>>>(c->tape_rs_bw, P, c->n_e, NCb, NT, c->n_a, 0, reinterpret_cast<int*>(c->tape_rs_bw + bwb));
     c->launches += 2; c->tape_rs_bw_nt = NT;
+    if (st) {
+      int* info = reinterpret_cast<int*>(c->tape_rs_bw + tape_rs_info_offset(c, false));
+      int* cnt = reinterpret_cast<int*>(c->tape_rs_bw + tape_rs_cnt_offset(c, false));
+      cudaMemsetAsync(info, 0, n * sizeof(int), c->stream);
+      cudaMemsetAsync(cnt, 0, (size_t)P * NCb * sizeof(int), c->stream);
+      k_rs_st_mark_bw<<<grid, 256, 0, c->stream>>>(c->tape_rs_bw, P, c->n_e, NCb, NT, c->n_a, info);
+      k_rs_st_count_bw<<<grid, 256, 0, c->stream>>>(info, P, c->n_e, NCb, NT, cnt);
+      c->launches += 2;
+    }
   }
   if (forward && c->tape_rs_fw_nt != NT) {
     k_tape_rowblocks_fw<<<grid, 256, 0, c->stream>>>(c->tape.fw, c->tape_rs_fw, P * c->n_e, c->n_e, c->lda, NT);
     k_rs_ranges<<<rgrid, 256, 0, c->stream>>>(c->tape_rs_fw, P, c->n_e, NCb, NT, c->n_a, 1, reinterpret_cast<int*>(c->tape_rs_fw + fwb));
     c->launches += 2; c->tape_rs_fw_nt = NT;
+    if (st) {
+      int* info = reinterpret_cast<int*>(c->tape_rs_fw + tape_rs_info_offset(c, true));
+      int* cnt = reinterpret_cast<int*>(c->tape_rs_fw + tape_rs_cnt_offset(c, true));
+      cudaMemsetAsync(info, 0xFF, n * sizeof(int), c->stream);
+      cudaMemsetAsync(cnt, 0, (size_t)P * NCb * sizeof(int), c->stream);
+      k_rs_st_mark_fw<<<grid, 256, 0, c->stream>>>(c->tape_rs_fw, P, c->n_e, NCb, NT, c->n_a, info, cnt);
+      c->launches++;
+    }
   }
   return cuda_check(c, cudaGetLastError(), "k_tape_rowblocks");
 }
@@ -55,7 +80,19 @@ static int bt_rs_launch(hank_ctx* c, int P, int K, const double* dr, const doubl
   const size_t slot = (size_t)GC * rs_bw_col_bytes<NT>();
   // one lane, a whole period per exchange: the push kernels (hank_tangent_rowsplit.cuh) where their buffers fit
   if constexpr (L == 1 && GC == NE && LA == 0 && NE * NT + 64 <= 1024) {
-    static const bool no_push = getenv("HANK_NO_RS_PUSH") != nullptr;
+    static const bool no_push = getenv("HANK_NO_RS_PUSH") != nullptr, no_st = getenv("HANK_NO_RS_ST") != nullptr;
+    if constexpr (NT == 64 && NC <= 8) {   // every thread sends its own value with st.async
+      const int Ss = rs_ring_slots(c, rs_bw_st_smem<NE, NC, NT>(0), rs_bw_st_slot<NE, NC, NT>(), 2, 6);
+      if (!no_push && !no_st && Ss >= 2) {
+        int rc = ensure_tape_rs(c, P, NT, false);
+        if (rc) return rc;
+        rc = launch_cluster_grid(c, KIND_BT, k_backward_tangent_rs_st<NE, NC, NT>, ncl * NC, NC, NE * NT + 32, rs_bw_st_smem<NE, NC, NT>(Ss),
+                                 "k_backward_tangent_rs_st", M, c->tape, (const unsigned char*)c->tape_rs_bw,
+                                 reinterpret_cast<const int*>(c->tape_rs_bw + tape_rs_info_offset(c, false)),
+                                 reinterpret_cast<const int*>(c->tape_rs_bw + tape_rs_cnt_offset(c, false)), (const int*)c->d_status, K, Ss, c->pass_thi, dr, dw, dpol);
+        if (rc >= 0) return rc;
+      }
+    }
     const int Sp = rs_ring_slots(c, rs_bw_push_smem<NE, NC, NT>(0), slot + 16, 2, 6);
     if (!no_push && Sp >= 2) {
       int rc = ensure_tape_rs(c, P, NT, false);
@@ -84,7 +121,20 @@ static int ft_rs_launch(hank_ctx* c, int P, int K, const double* dpol, double* d
   const size_t slot = (size_t)GC * rs_fw_col_bytes<NT, L>();
   // one lane, a whole period per exchange: a thread per (income state, row) instead of per row (hank_tangent_rowsplit.cuh)
   if constexpr (L == 1 && GC == NE && LA == 0 && NE * NT + 64 <= 1024) {
-    static const bool no_push = getenv("HANK_NO_RS_PUSH") != nullptr;
+    static const bool no_push = getenv("HANK_NO_RS_PUSH") != nullptr, no_st = getenv("HANK_NO_RS_ST") != nullptr;
+    if constexpr (NT == 64 && NC <= 8) {   // every thread sends its own masses with st.async
+      const int Ss = rs_ring_slots(c, rs_fw_st_smem<NE, NC, NT>(0), rs_fw_st_slot<NE, NC, NT>(), 2, 6);
+      if (!no_push && !no_st && Ss >= 2) {
+        int rc = ensure_tape_rs(c, P, NT, true);
+        if (rc) return rc;
+        rc = launch_cluster_grid(c, KIND_FT, k_forward_tangent_rs_st<NE, NC, NT>, ncl * NC, NC, NE * NT + 32, rs_fw_st_smem<NE, NC, NT>(Ss),
+                                 "k_forward_tangent_rs_st", M, (const unsigned char*)c->tape_rs_fw,
+                                 reinterpret_cast<const int*>(c->tape_rs_fw + tape_rs_info_offset(c, true)),
+                                 reinterpret_cast<const int*>(c->tape_rs_fw + tape_rs_cnt_offset(c, true)), (const int*)c->d_status, K, Kp, Ss, c->pass_thi,
+                                 (const double*)c->d_zero, dpol, pd_rs ? 1 : 0, dkdpart);
+        if (rc >= 0) return rc;
+      }
+    }
     const int Sp = rs_ring_slots(c, rs_fw_push_smem<NE, NC, NT>(0), slot + 16, 2, 6);
     if (!no_push && Sp >= 2) {
       int rc = ensure_tape_rs(c, P, NT, true);

@@ -1071,6 +1071,354 @@ k_backward_tangent_rs_push(const Consts<NE> M, const Tape tp, const unsigned cha
 }
 
 // ======================================================================================
+// One-lane sweeps whose threads push their OWN values (k_backward_tangent_rs_st, k_forward_tangent_rs_st).
+//
+// The bulk-copy push above still pays fence.proxy.async + a named barrier + the copy engine's issue latency per period,
+// and it moves whole blocks (3.5 / 7 KB per destination) through the ~20 B/clk DSMEM port when a neighbour needs a few
+// boundary rows.  But where a value has to go is known from the primal tape: in the forward sweep the mass x of source
+// q feeds exactly one destination row (the one whose x-range holds q) and y exactly one; in the backward sweep k̇ of
+// row g is read by the rows whose knots are g-1 or g (their owners: a bit mask).  k_rs_st_mark_* tabulate that per
+// (period, income state, source row) once per linearisation, together with the number of values every CTA receives per
+// period.  In the sweep each compute thread sends its value(s) with st.async (8 bytes, complete_tx on the destination's
+// mbarrier) straight from its registers into the destination's full-width buffer — no staging, no proxy fence, no
+// pushing warp — and the readers wait on their own mbarrier for (values + NC tokens) x 8 bytes and gather locally.
+// The NC tokens (one from every CTA of the cluster, sent by threads that have passed the period's CTA barrier) keep
+// any CTA at most one period ahead of any other, which is what makes the two-deep buffers and the two-phase barrier
+// safe.  Arithmetic and summation order are those of k_forward_tangent_rs_ce / k_backward_tangent_rs_push.
+// ======================================================================================
+// backward: info[(t*NC+s)*NE+e][r] |= 1 << owner of every live row whose knots i, i+1 include row s*NT+r
+static __global__ void k_rs_st_mark_bw(const unsigned char* __restrict__ tape_rs, int P, int NE, int NC, int NT, int n_a,
+                                       int* __restrict__ info) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)P * NC * NE * NT) return;
+  const int r = (int)(i % NT);
+  const size_t col = i / NT;                         // (t*NC + d)*NE + e
+  const int e = (int)(col % NE);
+  const size_t td = col / NE;
+  const int d = (int)(td % NC);
+  const size_t t = td / NC;
+  if (d * NT + r >= n_a) return;
+  const size_t colb = (size_t)BW_NF * NT * 8 + (size_t)NT * 4;
+  const int i0 = reinterpret_cast<const int*>(tape_rs + col * colb + (size_t)BW_NF * NT * 8)[r];
+  for (int k = i0; k <= i0 + 1; ++k)
+    if (k >= 0 && k < NC * NT) atomicOr(&info[((t * NC + k / NT) * NE + e) * NT + k % NT], 1 << d);
+}
+// cnt[t*NC+d] += number of set bits d among the sources of period t (NC*NE*NT is a multiple of 32: a warp has one t)
+static __global__ void k_rs_st_count_bw(const int* __restrict__ info, int P, int NE, int NC, int NT, int* __restrict__ cnt) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t per_t = (size_t)NC * NE * NT, total = (size_t)P * per_t;
+  const int mask = i < total ? info[i] : 0;
+  const size_t t = (i - (threadIdx.x & 31)) / per_t;
+  for (int d = 0; d < NC; ++d) {
+    const unsigned bal = __ballot_sync(0xffffffffu, (mask >> d) & 1);
+    if ((threadIdx.x & 31) == 0 && bal && t < (size_t)P) atomicAdd(&cnt[t * NC + d], __popc(bal));
+  }
+}
+// forward: byte 0 of info[...source...] = owner of the row whose x-range holds the source, byte 1 likewise for y
+// (bytes preset to 0xFF: nobody); cnt[t*NC+d] += sources of the rows of CTA d
+static __global__ void k_rs_st_mark_fw(const unsigned char* __restrict__ tape_rs, int P, int NE, int NC, int NT, int n_a,
+                                       int* __restrict__ info, int* __restrict__ cnt) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)P * NC * NE * NT) return;
+  const int r = (int)(i % NT);
+  const size_t col = i / NT;
+  const int e = (int)(col % NE);
+  const size_t td = col / NE;
+  const int d = (int)(td % NC);
+  const size_t t = td / NC;
+  if (d * NT + r >= n_a) return;
+  const size_t colb = (size_t)FW_NF * NT * 8 + (size_t)(NT + 4) * 4;
+  const int* ints = reinterpret_cast<const int*>(tape_rs + col * colb + (size_t)FW_NF * NT * 8) + r + 1;
+  const int s0 = max(ints[0], 0), s1 = ints[1], s2 = min(ints[2], NC * NT);
+  unsigned char* b = reinterpret_cast<unsigned char*>(info);
+  for (int q = s0; q < s1; ++q) b[(((t * NC + q / NT) * NE + e) * NT + q % NT) * 4] = (unsigned char)d;
+  for (int q = s1; q < s2; ++q) b[(((t * NC + q / NT) * NE + e) * NT + q % NT) * 4 + 1] = (unsigned char)d;
+  if (s2 > s0) atomicAdd(&cnt[t * NC + d], s2 - s0);
+}
+
+template <int NE, int NC, int NT> constexpr size_t rs_fw_st_slot() { return (size_t)NE * rs_fw_col_bytes<NT, 1>() + (size_t)NE * NT * 4; }
+template <int NE, int NC, int NT>
+constexpr size_t rs_fw_st_smem(int S) {   // ring | xy[2][2][NE][LDA] | mix[NE NT] | red | tok[2][NC] | barriers
+  return (size_t)S * rs_fw_st_slot<NE, NC, NT>() + (size_t)2 * 2 * NE * NC * NT * 8 + (size_t)NE * NT * 8 + (size_t)2 * (NE * NT / 32) * 8 +
+         (size_t)2 * NC * 8 + (size_t)(2 * S + 2) * 8 + 128;
+}
+template <int NE, int NC, int NT>
+__global__ void __launch_bounds__(NE * NT + 32, 1)
+k_forward_tangent_rs_st(const Consts<NE> M, const unsigned char* __restrict__ tape_rs, const int* __restrict__ info,
+                        const int* __restrict__ cnt, const int* __restrict__ status, int K, int Kp, int S, const int* __restrict__ thi,
+                        const double* __restrict__ zeros, const double* __restrict__ dpol, int pd_rs, double* __restrict__ dkdpart) {
+  constexpr int LDA = NC * NT, NTC = NE * NT, NWC = NTC / 32;
+  // a primal sweep that reported an error (a policy that is not monotone in a, ...) leaves a tape whose destinations and
+  // counts do not add up: every CTA of every cluster skips the sweep, the caller reads the status after the pass
+  if (status[0] != 0) return;
+  constexpr int COLB = (int)rs_fw_tape_col_bytes<NT>(), COLD = COLB / 8;
+  constexpr int ST_OFF = FW_NF * NT, PD_OFF = NE * COLD, IN_OFF = PD_OFF + NE * NT, SLOTD = IN_OFF + NE * NT / 2;
+  constexpr int XYD = NE * LDA;                     // one of x, y of one buffer
+  static_assert(NT % 32 == 0 && NC <= 32 && (NE * NT) % 4 == 0, "shape");
+  extern __shared__ __align__(128) unsigned char smem_rs[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_rank();
+  const int cluster = blockIdx.x / NC, ncl = gridDim.x / NC;
+  const int lane0 = cluster;
+  const int P = M.P;
+  double* ring = reinterpret_cast<double*>(smem_rs);
+  double* xy = ring + (size_t)S * SLOTD;
+  double* mix = xy + (size_t)4 * XYD;
+  double* red = mix + NTC;
+  double* tok = red + 2 * NWC;
+  uint64_t* full = reinterpret_cast<uint64_t*>(tok + 2 * NC);
+  uint64_t* empty = full + S;
+  uint64_t* xbar = empty + S;
+  const int pe = thi ? min(P, thi[lane0 / kThiGroup]) : P;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWC); }
+    mbar_init(&xbar[0], 1); mbar_init(&xbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  cluster_sync_all();
+
+  if (warp == NWC) {
+    // ---- producer warp: tape columns of this CTA's rows, ṗ of the lane, destinations of its sources
+    Cursor cs;
+    for (int t = 0; t < P; ++t) {
+      double* dst = ring + (size_t)cs.i * SLOTD;
+      constexpr uint32_t PDB = (uint32_t)(NE * NT * 8), INB = (uint32_t)(NE * NT * 4);
+      if (lane == 0) {
+        if (t >= S) mbar_wait(&empty[cs.i], cs.par ^ 1);
+        mbar_expect_tx(&full[cs.i], (uint32_t)(NE * COLB) + PDB + INB);
+        bulk_g2s(dst, tape_rs + (((size_t)t * NC + rank) * NE) * COLB, (uint32_t)(NE * COLB), &full[cs.i]);
+        bulk_g2s(dst + IN_OFF, info + ((size_t)t * NC + rank) * NTC, INB, &full[cs.i]);
+        if (t >= pe) {
+          for (uint32_t o = 0; o < PDB; o += kZeroBytes)
+            bulk_g2s(dst + PD_OFF + o / 8, zeros, min(PDB - o, (uint32_t)kZeroBytes), &full[cs.i]);
+        } else if (pd_rs) {
+          bulk_g2s(dst + PD_OFF, dpol + ((((size_t)t * ncl + cluster) * NC + rank) * NE) * NT, PDB, &full[cs.i]);
+        }
+      }
+      __syncwarp();
+      if (t < pe && !pd_rs)
+        for (int i = lane; i < NE; i += 32)
+          bulk_g2s(dst + PD_OFF + (size_t)i * NT, dpol + ((((size_t)t * NE + i) * Kp + lane0) * LDA + rank * NT), NT * 8, &full[cs.i]);
+      cs.next(S);
+    }
+  } else {
+    const int e = tid / NT, row = tid - e * NT;
+    double pic[NE];
+#pragma unroll
+    for (int e1 = 0; e1 < NE; ++e1) pic[e1] = M.Pi[e1][e];
+    const uint32_t xy_s = smem_u32(xy), xbar_s = smem_u32(xbar);
+    const uint32_t mine_off = (uint32_t)(e * LDA + (int)rank * NT + row) * 8u;   // this source's place in a full-width array
+    const uint32_t tok_dst = tid < NC ? map_to_cta(smem_u32(tok) + rank * 8u, (uint32_t)tid) : 0u;
+    const uint32_t tok_bar = tid < NC ? map_to_cta(xbar_s, (uint32_t)tid) : 0u;
+    int cnt_next = (tid == 0 && P > 0) ? __ldg(cnt + rank) : 0;
+    double Dd = 0.0;
+    Cursor sl_c;
+    for (int t = 0; t < P; ++t) {
+      const int b = t & 1;
+      if (tid == 0) {
+        mbar_expect_tx(&xbar[b], (uint32_t)(cnt_next + NC) * 8u);
+        if (t + 1 < P) cnt_next = __ldg(cnt + (size_t)(t + 1) * NC + rank);
+      }
+      const double* sl = ring + (size_t)sl_c.i * SLOTD;
+      mbar_wait(&full[sl_c.i], sl_c.par);
+      const double pd = sl[PD_OFF + e * NT + row];
+      const double om = sl[e * COLD + FW_OM * NT + row], dco = sl[e * COLD + FW_DCO * NT + row];
+      const double Dn = sl[e * COLD + FW_D * NT + row], pv = sl[e * COLD + FW_P * NT + row];
+      const int* sst = reinterpret_cast<const int*>(sl + e * COLD + ST_OFF) + row + 1;
+      const int s0 = sst[0], s1 = sst[1], s2 = sst[2];
+      const int inf = reinterpret_cast<const int*>(sl + IN_OFF)[e * NT + row];
+      __syncwarp();
+      if (lane == 0) mbar_arrive_local(&empty[sl_c.i]);   // everything this warp needs of the slot is in registers
+      // ---- the masses of this source go to the owners of their destination rows
+      const double xd = fma(om, Dd, dco * pd);
+      const uint32_t dx = (uint32_t)inf & 255u, dy = ((uint32_t)inf >> 8) & 255u;
+      const uint32_t xoff = xy_s + (uint32_t)(b * 2 * XYD) * 8u + mine_off;
+      if (dx < (uint32_t)NC) st_async_f64(map_to_cta(xoff, dx), xd, map_to_cta(xbar_s + 8u * (uint32_t)b, dx));
+      if (dy < (uint32_t)NC) st_async_f64(map_to_cta(xoff + (uint32_t)XYD * 8u, dy), Dd - xd, map_to_cta(xbar_s + 8u * (uint32_t)b, dy));
+      if (tid < NC) st_async_f64(tok_dst + (uint32_t)(b * NC) * 8u, 0.0, tok_bar + 8u * (uint32_t)b);
+      double kacc = pd * Dn;
+      // ---- the sources of this destination row, now in this CTA's buffer
+      mbar_wait_cluster(&xbar[b], (uint32_t)((t >> 1) & 1));
+      const double* xb = xy + (size_t)(b * 2) * XYD + e * LDA;
+      const double* yb = xb + XYD;
+      const int n1 = s1 - s0, n2 = s2 - s1;
+      double acc = 0.0;                         // 0 + x0 + y0 + x1 + y1 + the rest of x, then of y: gather_row's order
+      if (n1 > 0) acc = xb[s0];
+      if (n2 > 0) acc += yb[s1];
+      if (n1 > 1) acc += xb[s0 + 1];
+      if (n2 > 1) acc += yb[s1 + 1];
+      const int mx = max(n1, n2) - 2;
+      if (__any_sync(0xffffffffu, mx > 0)) {
+        constexpr int kSerial = 8;
+        if (mx > 0 && mx <= kSerial) {
+          for (int q = s0 + 2; q < s1; ++q) acc += xb[q];
+          for (int q = s1 + 2; q < s2; ++q) acc += yb[q];
+        }
+        unsigned bal = __ballot_sync(0xffffffffu, mx > kSerial);
+        while (bal) {                            // long ranges (the mass at the borrowing constraint): the whole warp
+          const int src = __ffs(bal) - 1;
+          bal &= bal - 1;
+          const int b0 = __shfl_sync(0xffffffffu, s0, src), b1 = __shfl_sync(0xffffffffu, s1, src), b2 = __shfl_sync(0xffffffffu, s2, src);
+          double v = 0.0;
+          for (int q = b0 + 2 + lane; q < b1; q += 32) v += xb[q];
+          for (int q = b1 + 2 + lane; q < b2; q += 32) v += yb[q];
+          v = warp_sum(v);
+          if (lane == src) acc += v;
+        }
+      }
+      // ---- Markov mix across the income states of the row and <p_t, Ḋ_t>
+      mix[e * NT + row] = acc;
+      named_bar_sync(2, NTC);
+      if (t > 0 && tid == 0 && lane0 < K) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NWC; ++w) s += red[((t - 1) & 1) * NWC + w];
+        dkdpart[((size_t)lane0 * P + (t - 1)) * NC + rank] = s;
+      }
+      double d = 0.0;
+#pragma unroll
+      for (int e1 = 0; e1 < NE; ++e1) d = fma(pic[e1], mix[e1 * NT + row], d);
+      Dd = d;
+      kacc = fma(pv, d, kacc);
+      const double s = warp_sum(kacc);
+      if (lane == 0) red[(t & 1) * NWC + warp] = s;
+      sl_c.next(S);
+    }
+    named_bar_sync(3, NTC);
+    if (tid == 0 && lane0 < K && P > 0) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < NWC; ++w) s += red[((P - 1) & 1) * NWC + w];
+      dkdpart[((size_t)lane0 * P + (P - 1)) * NC + rank] = s;
+    }
+  }
+  __syncwarp();
+  cluster_sync_all();
+}
+
+template <int NE, int NC, int NT> constexpr size_t rs_bw_st_slot() { return (size_t)NE * rs_bw_col_bytes<NT>() + (size_t)NE * NT * 4; }
+template <int NE, int NC, int NT>
+constexpr size_t rs_bw_st_smem(int S) {   // ring | kd[2][NE][LDA] | mixv[NE NT] | tok[2][NC] | barriers
+  return (size_t)S * rs_bw_st_slot<NE, NC, NT>() + (size_t)2 * NE * NC * NT * 8 + (size_t)NE * NT * 8 + (size_t)2 * NC * 8 +
+         (size_t)(2 * S + 2) * 8 + 128;
+}
+template <int NE, int NC, int NT>
+__global__ void __launch_bounds__(NE * NT + 32, 1)
+k_backward_tangent_rs_st(const Consts<NE> M, const Tape tp, const unsigned char* __restrict__ tape_rs, const int* __restrict__ info,
+                         const int* __restrict__ cnt, const int* __restrict__ status, int K, int S, const int* __restrict__ thi,
+                         const double* __restrict__ dr, const double* __restrict__ dw, double* __restrict__ dpol) {
+  constexpr int LDA = NC * NT, NTC = NE * NT, NWC = NTC / 32;
+  if (status[0] != 0) return;   // (see k_forward_tangent_rs_st)
+  constexpr int COLB = (int)rs_bw_col_bytes<NT>(), COLD = COLB / 8, IN_OFF = NE * COLD, SLOTD = IN_OFF + NE * NT / 2;
+  constexpr int KD = NE * LDA;
+  static_assert(NT % 32 == 0 && NC <= 32 && (NE * NT) % 4 == 0, "shape");
+  extern __shared__ __align__(128) unsigned char smem_rs[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_rank();
+  const int cluster = blockIdx.x / NC, ncl = gridDim.x / NC;
+  const int lane0 = cluster;
+  const int Pfull = M.P, P = thi ? min(M.P, thi[lane0 / kThiGroup]) : M.P, n_a = M.n_a;
+  double* ring = reinterpret_cast<double*>(smem_rs);
+  double* kdb = ring + (size_t)S * SLOTD;
+  double* mixv = kdb + (size_t)2 * KD;
+  double* tok = mixv + NTC;
+  uint64_t* full = reinterpret_cast<uint64_t*>(tok + 2 * NC);
+  uint64_t* empty = full + S;
+  uint64_t* xbar = empty + S;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWC); }
+    mbar_init(&xbar[0], 1); mbar_init(&xbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  cluster_sync_all();
+
+  if (warp == NWC) {
+    if (lane == 0) {   // ---- producer: this CTA's rows of the period's tape and the readers of its rows
+      Cursor cs;
+      constexpr uint32_t INB = (uint32_t)(NE * NT * 4);
+      for (int it = 0; it < P; ++it) {
+        const int t = P - 1 - it;
+        if (it >= S) mbar_wait(&empty[cs.i], cs.par ^ 1);
+        mbar_expect_tx(&full[cs.i], (uint32_t)(NE * COLB) + INB);
+        bulk_g2s(ring + (size_t)cs.i * SLOTD, tape_rs + (((size_t)t * NC + rank) * NE) * COLB, (uint32_t)(NE * COLB), &full[cs.i]);
+        bulk_g2s(ring + (size_t)cs.i * SLOTD + IN_OFF, info + ((size_t)t * NC + rank) * NTC, INB, &full[cs.i]);
+        cs.next(S);
+      }
+    }
+  } else {
+    const int e = tid / NT, row = tid - e * NT;
+    const bool live = (int)rank * NT + row < n_a;
+    double pir[NE];                                   // Π[e, ·]
+#pragma unroll
+    for (int e2 = 0; e2 < NE; ++e2) pir[e2] = M.Pi[e][e2];
+    const double ze = M.z[e];
+    const bool on = lane0 < K && P > 0;
+    const uint32_t kd_s = smem_u32(kdb), xbar_s = smem_u32(xbar);
+    const uint32_t mine_off = (uint32_t)(e * LDA + (int)rank * NT + row) * 8u;
+    const uint32_t tok_dst = tid < NC ? map_to_cta(smem_u32(tok) + rank * 8u, (uint32_t)tid) : 0u;
+    const uint32_t tok_bar = tid < NC ? map_to_cta(xbar_s, (uint32_t)tid) : 0u;
+    int cnt_next = (tid == 0 && P > 0) ? __ldg(cnt + (size_t)(P - 1) * NC + rank) : 0;
+    double Vd = 0.0;
+    double rho = __ldg(tp.rho + (P > 0 ? P - 1 : 0));
+    double drn = on ? __ldg(dr + (size_t)lane0 * Pfull + P - 1) : 0.0, dwn = on ? __ldg(dw + (size_t)lane0 * Pfull + P - 1) : 0.0;
+    Cursor sl_c;
+    for (int it = 0; it < P; ++it) {
+      const int t = P - 1 - it, b = it & 1;
+      const double rho_t = rho, drl = drn, dwl = dwn;
+      if (t > 0) {
+        rho = __ldg(tp.rho + t - 1);
+        drn = on ? __ldg(dr + (size_t)lane0 * Pfull + t - 1) : 0.0;
+        dwn = on ? __ldg(dw + (size_t)lane0 * Pfull + t - 1) : 0.0;
+      }
+      // ---- ĖV of this income state: the row's V̇ of all income states meet in shared memory
+      mixv[e * NT + row] = Vd;
+      named_bar_sync(3, NTC);          // (every thread of the CTA is through the previous period's reads from here on)
+      if (tid == 0) {
+        mbar_expect_tx(&xbar[b], (uint32_t)(cnt_next + NC) * 8u);
+        if (t > 0) cnt_next = __ldg(cnt + (size_t)(t - 1) * NC + rank);
+      }
+      double ev = 0.0;
+#pragma unroll
+      for (int e2 = 0; e2 < NE; ++e2) ev = fma(pir[e2], mixv[e2 * NT + row], ev);
+      // ---- k̇ of this (row, income state), sent to the owners of the rows that interpolate on it
+      const double* sl = ring + (size_t)sl_c.i * SLOTD + e * COLD + row;
+      mbar_wait(&full[sl_c.i], sl_c.par);
+      const double a1 = sl[BW_A1 * NT], kr = sl[BW_KR * NT];
+      const double cA = sl[BW_CA * NT], cB = sl[BW_CB * NT], E1 = sl[BW_E1 * NT], vf = sl[BW_VF * NT];
+      const int i0 = reinterpret_cast<const int*>(sl - row + BW_NF * NT)[row];
+      unsigned mk = (unsigned)reinterpret_cast<const int*>(ring + (size_t)sl_c.i * SLOTD + IN_OFF)[e * NT + row];
+      __syncwarp();
+      if (lane == 0) mbar_arrive_local(&empty[sl_c.i]);
+      const double kd = fma(a1, ev, fma(kr, drl, -(rho_t * ze) * dwl));
+      const uint32_t koff = kd_s + (uint32_t)(b * KD) * 8u + mine_off;
+      while (mk) {
+        const uint32_t d = (uint32_t)__ffs((int)mk) - 1u;
+        mk &= mk - 1u;
+        st_async_f64(map_to_cta(koff, d), kd, map_to_cta(xbar_s + 8u * (uint32_t)b, d));
+      }
+      if (tid < NC) st_async_f64(tok_dst + (uint32_t)(b * NC) * 8u, 0.0, tok_bar + 8u * (uint32_t)b);
+      // ---- ṗ and V̇ from k̇ at the two knots
+      mbar_wait_cluster(&xbar[b], (uint32_t)((it >> 1) & 1));
+      const double* kb = kdb + (size_t)b * KD + e * LDA;
+      const double k0 = live ? kb[i0] : 0.0;
+      const double k1 = live ? kb[i0 + 1] : 0.0;
+      const double pd = fma(cA, k0, cB * k1);
+      __stcs(dpol + (((size_t)t * ncl + cluster) * NC + rank) * (size_t)(NE * NT) + e * NT + row, pd);
+      Vd = fma(vf, fma(ze, dwl, -pd), E1 * drl);
+      sl_c.next(S);
+    }
+  }
+  __syncwarp();
+  cluster_sync_all();
+}
+
+// ======================================================================================
 // Row-block-major copies of the primal tape for the kernels above (see the header comment).
 // One thread per (column, row): the row's coefficients and index / range start.
 // ======================================================================================
