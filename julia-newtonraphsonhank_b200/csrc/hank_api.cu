@@ -52,6 +52,11 @@ __global__ void k_extract_rw(const double* __restrict__ x, int P, double* r, dou
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < P) { r[t] = x[4 * t + 2]; w[t] = x[4 * t + 3]; }
 }
+// 1/(1+r): what the backward primal sweep writes per period, in place before a tangent sweep starts next to it
+__global__ void k_fill_rho(const double* __restrict__ r, int P, double* rho) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < P) { const double opr = 1.0 + r[t]; rho[t] = 1.0 / opr; }
+}
 // V: n x K column-major (lane-major); dr, dw: [K][P]
 __global__ void k_extract_drdw(const double* __restrict__ V, int P, int K, double* dr, double* dw) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -210,6 +215,9 @@ static int sw_backward_tangent(hank_ctx* c, int P, int K, const double* dr, cons
                                const double* dvalT, double* dpol, double* dvf) {
   NE_DISPATCH(c, backward_tangent(c, P, K, dr, dw, dvalT, dpol, dvf));
 }
+static int sw_primal_both(hank_ctx* c, int P, const double* vT, const double* r, const double* w, const double* D0) {
+  NE_DISPATCH(c, primal_both(c, P, vT, r, w, D0));
+}
 static int sw_forward_primal(hank_ctx* c, int P, const double* D0, const double* pol, double* KD) {
   NE_DISPATCH(c, forward_primal(c, P, D0, pol, KD));
 }
@@ -238,8 +246,9 @@ static int join_side(hank_ctx* c) {
   if (c->fp_pending) {
     CK(cudaStreamWaitEvent(c->stream, c->ev_fp, 0));
     c->fp_pending = false;
+    c->bp_pending = false;   // (the forward sweep was queued behind the backward primal sweep on the same stream)
   }
-  return HANK_OK;
+  return join_bp(c);
 }
 
 static int check_status(hank_ctx* c) {
@@ -373,6 +382,7 @@ static int tangent_pass(hank_ctx* c, int P, int K) {
   // clusters does both of its sweeps in that tail (0.25 + 0.39 ms at 500x7) before the main forward sweep needs
   // every SM again.
   cudaStream_t main_s = c->stream;
+  if (c->bp_pending) CK(cudaStreamWaitEvent(c->stream3, c->ev_bpd, 0));   // (pipelined linearisation: only the main wave follows the primal sweep)
   CK(cudaEventRecord(c->ev_v, main_s));                   // seeds, horizons and the backward tape are in place
   CK(cudaStreamWaitEvent(c->stream3, c->ev_v, 0));
   c->pass_Kp = K1;
@@ -470,6 +480,8 @@ int hank_ctx_create(hank_ctx** out, int device, int n_a, int n_e, int T, const d
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CK(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, hi));
     CK(cudaEventCreateWithFlags(&c->ev_bp, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_bps, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_bpd, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_fp, cudaEventDisableTiming));
     CK(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->ev_v, cudaEventDisableTiming));
@@ -497,6 +509,9 @@ int hank_ctx_create(hank_ctx** out, int device, int n_a, int n_e, int T, const d
   RC(dalloc(c, &c->d_zero, (size_t)kZeroBytes / sizeof(double)));
   CK(cudaMemsetAsync(c->d_zero, 0, kZeroBytes, c->stream));
   RC(dalloc(c, &c->d_status, 4));
+  RC(dalloc(c, &c->d_bpflag, 16));
+  CK(cudaMemset(c->d_bpflag, 0, 16 * sizeof(int)));
+  c->no_pipe = getenv("HANK_NO_PIPE") != nullptr;
   CK(cudaMemset(c->d_status, 0, 4 * sizeof(int)));
   CK(cudaMallocHost((void**)&c->h_status, 4 * sizeof(int)));
   const size_t n = (size_t)4 * c->P;
@@ -512,6 +527,9 @@ void hank_ctx_destroy(hank_ctx* c) {
   if (c->ev_v) cudaEventDestroy(c->ev_v);
   if (c->ev_x) cudaEventDestroy(c->ev_x);
   if (c->ev_bp) cudaEventDestroy(c->ev_bp);
+  if (c->ev_bps) cudaEventDestroy(c->ev_bps);
+  if (c->ev_bpd) cudaEventDestroy(c->ev_bpd);
+  dfree(c->d_bpflag);
   if (c->ev_fp) cudaEventDestroy(c->ev_fp);
   hank_comm_destroy(c);
   newton_release(c);
@@ -924,16 +942,49 @@ int hank_ks_linearize_dev(hank_ctx* c, const double* x, const double* Z, double*
   if (Z != c->d_Z) CK(cudaMemcpyAsync(c->d_Z, Z, (size_t)c->n_exog * P * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   if (c->eq_on) RC(eq_extract_rw(c, c->d_x, c->d_r, c->d_w));
   else { k_extract_rw<<<nblk(P), 256, 0, c->stream>>>(c->d_x, P, c->d_r, c->d_w); c->launches++; }
-  RC(backward_dev(c, c->d_r, c->d_w, 0, nullptr, nullptr));
   // The forward primal sweep and the residuals only feed the forward tangent / F: they go to the
-  // high-priority side stream so that a following backward tangent sweep overlaps them.
+  // high-priority side stream so that a following backward tangent sweep overlaps them.  Pipelined linearisation
+  // (hank_ctx.h): the backward primal sweep goes there too, and a backward tangent sweep of the one-CTA ring kernel
+  // launched next may run alongside it, following its progress counters; everything else joins first (join_bp).
   cudaStream_t main_stream = c->stream;
-  if (!c->no_overlap) {
+  const bool pipe = !c->no_overlap && !c->no_pipe && c->stream2 && c->d_bpflag;
+  bool fused = false;
+  if (pipe) {
+    k_fill_rho<<<nblk(P), 256, 0, main_stream>>>(c->d_r, P, c->tape.rho);
+    c->launches++;
     CK(cudaEventRecord(c->ev_bp, main_stream));
     CK(cudaStreamWaitEvent(c->stream2, c->ev_bp, 0));
     c->stream = c->stream2;
+    int rcb = -1;
+    // a many-lane tangent pass followed the last linearisation (pipe_hint): both primal sweeps in one launch, so that the
+    // cluster's SMs are not taken by that pass's pending CTAs between the two sweeps
+    if (c->pipe_hint) {
+      rcb = sw_primal_both(c, P, c->d_valueT, c->d_r, c->d_w, c->d_D0);
+      if (rcb == 0) {
+        fused = true;
+        c->have_backward = true; c->K_last = 0;
+        k_reduce_partials<<<nblk(P), 256, 0, c->stream>>>(c->d_kdpart, c->n_e * (c->lda / 32), P, c->d_KD);
+        c->launches++;
+        rcb = cuda_check(c, cudaGetLastError(), "k_reduce_partials");
+        c->have_forward = true;
+      } else if (rcb > 0) { c->stream = main_stream; return rcb; }
+    }
+    if (!fused) {
+      c->bp_pipe_req = true;
+      rcb = backward_dev(c, c->d_r, c->d_w, 0, nullptr, nullptr);
+      c->bp_pipe_req = false;
+    }
+    if (rcb == HANK_OK) rcb = cuda_check(c, cudaEventRecord(c->ev_bpd, c->stream2), "cudaEventRecord(ev_bpd)");
+    if (rcb != HANK_OK) { c->stream = main_stream; cudaStreamWaitEvent(main_stream, c->ev_bpd, 0); return rcb; }
+  } else {
+    RC(backward_dev(c, c->d_r, c->d_w, 0, nullptr, nullptr));
+    if (!c->no_overlap) {
+      CK(cudaEventRecord(c->ev_bp, main_stream));
+      CK(cudaStreamWaitEvent(c->stream2, c->ev_bp, 0));
+      c->stream = c->stream2;
+    }
   }
-  int rc = forward_dev(c, c->tape.pol, 0, nullptr, c->d_KD, nullptr);
+  int rc = fused ? HANK_OK : forward_dev(c, c->tape.pol, 0, nullptr, c->d_KD, nullptr);
   if (rc == HANK_OK) {
     if (c->eq_on) rc = eq_residual(c, c->d_x, c->d_KD, c->d_Z, F);
     else {
@@ -944,6 +995,7 @@ int hank_ks_linearize_dev(hank_ctx* c, const double* x, const double* Z, double*
   }
   if (!c->no_overlap) {
     c->stream = main_stream;
+    c->bp_pending = pipe;   // (set here: the forward sweep above ran on the primal's own stream)
     if (rc == HANK_OK) { CK(cudaEventRecord(c->ev_fp, c->stream2)); c->fp_pending = true; }
   }
   RC(rc);

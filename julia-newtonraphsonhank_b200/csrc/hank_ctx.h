@@ -19,6 +19,14 @@ struct hank_ctx {
   cudaStream_t stream3 = nullptr;   // copy stream: tangent seeds upload overlapping the primal sweep
   cudaEvent_t ev_bp = nullptr, ev_fp = nullptr, ev_v = nullptr, ev_x = nullptr;   // ev_x: overflow lanes of a Jacobian pass done (stream3)
   bool fp_pending = false, no_overlap = false;
+  // Pipelined linearisation: the backward primal sweep runs on stream2 and publishes, per income state, how many
+  // periods of the backward tape are complete (d_bpflag); a backward tangent sweep of the one-CTA ring kernel may start
+  // as soon as the primal's CTAs are resident (ev_bps, a launch-completion event) and follows it through the flags.
+  // Every other reader of the backward tape waits for ev_bpd (join_bp).
+  int* d_bpflag = nullptr;
+  cudaEvent_t ev_bps = nullptr, ev_bpd = nullptr, next_launch_ev = nullptr;
+  bool bp_pending = false, bp_flags = false, bp_pipe_req = false, no_pipe = false;
+  bool pipe_hint = false;   // the last tangent pass followed a primal sweep in flight: fuse the next linearisation's primal sweeps
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int smem_max = 0, sm_count = 0;
 
@@ -122,6 +130,8 @@ struct Sweeps {
   static int backward_tangent(hank_ctx* c, int P, int K, const double* dr, const double* dw,
                               const double* dvalT, double* dpol, double* dvalue_first);
   static int forward_primal(hank_ctx* c, int P, const double* D0, const double* pol, double* KD);
+  // both primal sweeps in one cluster launch with progress counters (pipelined linearisation); -1: shape not available
+  static int primal_both(hank_ctx* c, int P, const double* valueT, const double* r, const double* w, const double* D0);
   static int forward_tangent(hank_ctx* c, int P, int K, const double* dpol, double* dkdpart, int* nw_out);
   static int lanes_per_cta(hank_ctx* c, int K);
   // rows of a lane group split over a cluster of NC CTAs (hank_tangent_rowsplit.cuh); -1: shape not available
@@ -137,6 +147,12 @@ cudaEvent_t prof_begin(hank_ctx* c);
 void prof_end(hank_ctx* c, int kind, cudaEvent_t a);
 int set_error(hank_ctx* c, int code, const std::string& msg);
 int cuda_check(hank_ctx* c, cudaError_t e, const char* what);
+// the backward primal sweep of a pipelined linearisation (stream2) must be complete before c->stream goes on
+static inline int join_bp(hank_ctx* c) {
+  if (!c->bp_pending) return 0;
+  c->bp_pending = false;
+  return cuda_check(c, cudaStreamWaitEvent(c->stream, c->ev_bpd, 0), "cudaStreamWaitEvent(ev_bpd)");
+}
 void newton_release(hank_ctx* c);   // destroys the cuSOLVER handle (hank_newton.cu)
 // generic equations (hank_eq.cu)
 int eq_extract_rw(hank_ctx* c, const double* x, double* r, double* w);

@@ -4,6 +4,7 @@
 #pragma once
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include "hank_ctx.h"
 #include "hank_tangent.cuh"
 #include "hank_tangent_tma.cuh"
@@ -57,12 +58,19 @@ static int launch_cluster(hank_ctx* c, int kind, KernelT kern, int block, size_t
   if (rc) return rc;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(NE); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = NE; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   int ncl = 0;
   if (cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg) != cudaSuccess || ncl < 1) { cudaGetLastError(); return -1; }
+  if (c->next_launch_ev) {   // fires once every CTA of this launch has begun execution (hank_ctx.h: ev_bps)
+    at[1].id = cudaLaunchAttributeLaunchCompletionEvent;
+    at[1].val.launchCompletionEvent.event = c->next_launch_ev;
+    at[1].val.launchCompletionEvent.flags = 0;
+    cfg.numAttrs = 2;
+    c->next_launch_ev = nullptr;
+  }
   cudaEvent_t ev = prof_begin(c);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args...);
   prof_end(c, kind, ev);
@@ -100,16 +108,25 @@ template <int NE, int R, int NT>
 static int bp_launch(hank_ctx* c, int P, const double* valueT, const double* r, const double* w) {
   const Consts<NE> M = make_consts<NE>(c, P);
   c->tape_rs_bw_nt = 0;
+  c->bp_flags = false;
   // exchange through distributed shared memory (hank_primal_dsmem.cuh); with two or more rows per thread the
   // per-row remote stores cost more than the fence they replace (1000x7: 4.16 vs 3.97 us per period)
   if constexpr (R == 1) if (!c->no_cluster && !c->no_dsmem && NE > 1 && bp_ds_smem<NE, NT * R>() <= (size_t)c->smem_max) {
     const size_t smem_d = bp_ds_smem<NE, NT * R>();
+    // a pipelined linearisation (hank_ctx.h): progress counters per income state + "all CTAs resident" event
+    int* flags = nullptr;
+    if (c->bp_pipe_req && c->d_bpflag) {
+      flags = c->d_bpflag;
+      if (cudaMemsetAsync(flags, 0, 16 * sizeof(int), c->stream) != cudaSuccess) { cudaGetLastError(); flags = nullptr; }
+    }
+    c->next_launch_ev = flags ? c->ev_bps : nullptr;
     int rc = c->gamma == 2.0
-        ? launch_cluster<NE>(c, KIND_BP, k_backward_primal_ds<NE, R, NT, true>, NT, smem_d, "k_backward_primal_ds", M, c->tape,
-                             (const double*)c->d_grid, valueT, r, w, c->d_status)
-        : launch_cluster<NE>(c, KIND_BP, k_backward_primal_ds<NE, R, NT, false>, NT, smem_d, "k_backward_primal_ds", M, c->tape,
-                             (const double*)c->d_grid, valueT, r, w, c->d_status);
-    if (rc >= 0) return rc;
+        ? launch_cluster<NE>(c, KIND_BP, k_backward_primal_ds<NE, R, NT, true>, NT + 32, smem_d, "k_backward_primal_ds", M, c->tape,
+                             (const double*)c->d_grid, valueT, r, w, c->d_status, flags)
+        : launch_cluster<NE>(c, KIND_BP, k_backward_primal_ds<NE, R, NT, false>, NT + 32, smem_d, "k_backward_primal_ds", M, c->tape,
+                             (const double*)c->d_grid, valueT, r, w, c->d_status, flags);
+    c->next_launch_ev = nullptr;
+    if (rc >= 0) { c->bp_flags = flags != nullptr && rc == 0; return rc; }
   }
   if (!c->no_cluster && NE > 1) {
     const size_t smem_c = (size_t)2 * NT * R * sizeof(double);
@@ -134,6 +151,33 @@ int Sweeps<NE>::backward_primal(hank_ctx* c, int P, const double* valueT, const 
   if (s.R == 1) return bp_launch<NE, 1, 512>(c, P, valueT, r, w);
   if (s.R == 2) return bp_launch<NE, 2, 512>(c, P, valueT, r, w);
   return bp_launch<NE, 4, 512>(c, P, valueT, r, w);
+}
+
+// ---- both primal sweeps, one launch (pipelined linearisation) ------------------------------
+template <int NE, int NT>
+static int pb_launch(hank_ctx* c, int P, const double* valueT, const double* r, const double* w, const double* D0) {
+  if (c->no_cluster || c->no_dsmem || NE <= 1 || !c->d_bpflag || fp_ds_smem<NE, NT>() > (size_t)c->smem_max) return -1;
+  const Consts<NE> M = make_consts<NE>(c, P);
+  const size_t smem = fp_ds_smem<NE, NT>() > bp_ds_smem<NE, NT>() ? fp_ds_smem<NE, NT>() : bp_ds_smem<NE, NT>();
+  if (cudaMemsetAsync(c->d_bpflag, 0, 16 * sizeof(int), c->stream) != cudaSuccess) { cudaGetLastError(); return -1; }
+  c->next_launch_ev = c->ev_bps;
+  int rc = c->gamma == 2.0
+      ? launch_cluster<NE>(c, KIND_BP, k_primal_ds_both<NE, 1, NT, true>, NT + 32, smem, "k_primal_ds_both", M, c->tape,
+                           (const double*)c->d_grid, valueT, r, w, c->d_status, c->d_bpflag, D0, c->d_kdpart)
+      : launch_cluster<NE>(c, KIND_BP, k_primal_ds_both<NE, 1, NT, false>, NT + 32, smem, "k_primal_ds_both", M, c->tape,
+                           (const double*)c->d_grid, valueT, r, w, c->d_status, c->d_bpflag, D0, c->d_kdpart);
+  c->next_launch_ev = nullptr;
+  if (rc != 0) return rc;
+  c->tape_rs_bw_nt = 0; c->tape_rs_fw_nt = 0;
+  c->bp_flags = true; c->fp_cluster = true;
+  return 0;
+}
+template <int NE>
+int Sweeps<NE>::primal_both(hank_ctx* c, int P, const double* valueT, const double* r, const double* w, const double* D0) {
+  Shape s;
+  if (!pick_shape(c->n_a, &s) || s.R != 1) return -1;
+  if (s.NT == 256) return pb_launch<NE, 256>(c, P, valueT, r, w, D0);
+  return pb_launch<NE, 512>(c, P, valueT, r, w, D0);
 }
 
 // ---- forward primal --------------------------------------------------------------------
@@ -267,10 +311,24 @@ static int bt_launch(hank_ctx* c, int P, int K, const double* dr, const double* 
   if constexpr (bt_ring_ne_smem<NE, LDA, L>() <= 232448 && L != 6 && L != 3)
     if (!c->no_tma && !c->no_ring_ne && dvalT == nullptr && dvf == nullptr && bt_ring_ne_smem<NE, LDA, L>() <= (size_t)c->smem_max) {
       const size_t smem_r = bt_ring_ne_smem<NE, LDA, L>();
-      if (c->pass_thi)
-        HANK_LAUNCH(KIND_BT, (k_backward_tangent_ring_ne<NE, R, NT, L, true>), grid, NT, smem_r, M, c->tape, K, Kp, c->pass_thi, dr, dw, dpol);
-      HANK_LAUNCH(KIND_BT, (k_backward_tangent_ring_ne<NE, R, NT, L, false>), grid, NT, smem_r, M, c->tape, K, Kp, (const int*)nullptr, dr, dw, dpol);
+      // next to a backward primal sweep still in flight (pipelined linearisation): start once its CTAs are resident
+      // and follow its progress counters; everything after this sweep is ordered behind the primal's completion
+      const bool pipe = c->bp_pending && c->bp_flags;
+      c->pipe_hint = true;   // (a pass of this kind can follow a primal sweep in flight: worth fusing the next one's)
+      const int* flags = pipe ? c->d_bpflag : nullptr;
+      static const bool nowait = getenv("HANK_PIPE_NOWAIT") != nullptr;
+      if (pipe && !nowait) { int rcw = cuda_check(c, cudaStreamWaitEvent(c->stream, c->ev_bps, 0), "cudaStreamWaitEvent(ev_bps)"); if (rcw) return rcw; }
+      else { int rcw = join_bp(c); if (rcw) return rcw; }
+      auto launch = [&]() -> int {
+        if (c->pass_thi)
+          HANK_LAUNCH(KIND_BT, (k_backward_tangent_ring_ne<NE, R, NT, L, true>), grid, NT, smem_r, M, c->tape, K, Kp, c->pass_thi, dr, dw, dpol, flags);
+        HANK_LAUNCH(KIND_BT, (k_backward_tangent_ring_ne<NE, R, NT, L, false>), grid, NT, smem_r, M, c->tape, K, Kp, (const int*)nullptr, dr, dw, dpol, flags);
+      };
+      const int rcl = launch();
+      if (pipe) { int rcw = join_bp(c); if (rcw) return rcw; }
+      return rcl;
     }
+  { int rcw = join_bp(c); if (rcw) return rcw; }
   if constexpr (LDA <= 1024) if (!c->no_tma) {  // TMA-staged tape ring (hank_tangent_tma.cuh)
     const size_t slot = bw_chunk_bytes<LDA>();
     const size_t fixed = (size_t)2 * L * LDA * 8 + (size_t)2 * L * P * 8 + (size_t)((P + 1) & ~1) * 8 + 16 * 8 + 128;
@@ -341,6 +399,8 @@ int Sweeps<NE>::backward_tangent(hank_ctx* c, int P, int K, const double* dr, co
   const bool allow_rs = dvalT == nullptr && dvf == nullptr;
   TangentCfg cfg = tangent_cfg<NE>(c, K, allow_rs);
   if (cfg.NC > 0) {
+    c->pipe_hint = false;
+    { int rcw = join_bp(c); if (rcw) return rcw; }
     const int rc = Sweeps<NE>::backward_tangent_rs(c, cfg.NC, cfg.NT, cfg.L, cfg.GC, P, K, dr, dw, dpol);
     if (rc >= 0) return rc;
     return set_error(c, 1, "row-split cluster launch of the backward tangent sweep failed (cluster not schedulable)");

@@ -4,5 +4,6 @@
 namespace hank {
 template int Sweeps<7>::backward_primal(hank_ctx*, int, const double*, const double*, const double*);
 template int Sweeps<7>::forward_primal(hank_ctx*, int, const double*, const double*, double*);
+template int Sweeps<7>::primal_both(hank_ctx*, int, const double*, const double*, const double*, const double*);
 template int Sweeps<7>::lanes_per_cta(hank_ctx*, int);
 }

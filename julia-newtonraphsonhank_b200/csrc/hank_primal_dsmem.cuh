@@ -65,11 +65,14 @@ constexpr size_t fp_ds_smem() { return ((size_t)2 * NE * LDA + 3 * LDA) * 8 + ((
 // ======================================================================================
 // Backward primal sweep.  smem: xb[2][NE][LDA] ∂V/∂a of all columns | ks[2][LDA] | g[LDA] | bar[2]
 // ======================================================================================
+// Launched with NT + 32 threads: the extra warp owns no rows.  It joins every CTA barrier and, when `flags` is given,
+// publishes after the barrier of iteration it that this CTA's column of the backward tape is complete for the first
+// `it` iterations (periods P-1 .. P-it): __threadfence + store, off the compute warps' critical path.  A backward
+// tangent sweep running NEXT TO this kernel follows those counters (k_backward_tangent_ring_ne, wait_tape_flag).
 template <int NE, int R, int NT, bool G2>
-__global__ void __launch_bounds__(NT, 1)
-k_backward_primal_ds(const Consts<NE> M, const Tape tp, const double* __restrict__ grid,
-                     const double* __restrict__ valueT, const double* __restrict__ rpath,
-                     const double* __restrict__ wpath, int* __restrict__ status) {
+__device__ __forceinline__ void bp_ds_body(const Consts<NE>& M, const Tape& tp, const double* __restrict__ grid,
+                                           const double* __restrict__ valueT, const double* __restrict__ rpath,
+                                           const double* __restrict__ wpath, int* __restrict__ status, int* __restrict__ flags) {
   constexpr int LDA = NT * R;
   constexpr size_t GP = (size_t)NE * LDA;
   extern __shared__ __align__(16) double smem_ds[];
@@ -108,6 +111,17 @@ k_backward_primal_ds(const Consts<NE> M, const Tape tp, const double* __restrict
     for (int c = 0; c < NE; ++c) { rdst[c] = map_to_cta(mine, c); rbar[c] = map_to_cta(b0, c); }
   }
   cluster.sync();   // every CTA's barriers exist before anyone sends
+  if (tid >= NT) {   // ---- the publishing warp
+    for (int it = 0; it <= P; ++it) {
+      __syncthreads();   // every row of this CTA is through iteration it-1
+      if (flags && tid == NT && it > 0) {
+        __threadfence();
+        *reinterpret_cast<volatile int*>(flags + e) = it;
+      }
+    }
+    cluster.sync();
+    return;
+  }
   const uint32_t col_bytes = (uint32_t)NE * (uint32_t)n_a * 8u;
   double rn = rpath[P - 1], wn = wpath[P - 1];
   double Vlast[R];
@@ -167,6 +181,7 @@ k_backward_primal_ds(const Consts<NE> M, const Tape tp, const double* __restrict
       }
     }
   }
+  __syncthreads();   // (the publishing warp's last count: all P periods of this column are written)
   // the last period's columns are still in flight towards this CTA: drain before anyone exits
   mbar_wait_cluster(&bar[(P - 1) & 1], ((P - 1) >> 1) & 1);
 #pragma unroll
@@ -175,17 +190,28 @@ k_backward_primal_ds(const Consts<NE> M, const Tape tp, const double* __restrict
     if (a < n_a) tp.value_first[(size_t)e * LDA + a] = Vlast[j];
   }
   cluster.sync();
+  if (tid == 0) {   // (k_primal_ds_both reuses this shared memory for the forward sweep)
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&bar[0])) : "memory");
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&bar[1])) : "memory");
+  }
+}
+template <int NE, int R, int NT, bool G2>
+__global__ void __launch_bounds__(NT + 32, 1)
+k_backward_primal_ds(const Consts<NE> M, const Tape tp, const double* __restrict__ grid,
+                     const double* __restrict__ valueT, const double* __restrict__ rpath,
+                     const double* __restrict__ wpath, int* __restrict__ status, int* __restrict__ flags) {
+  bp_ds_body<NE, R, NT, G2>(M, tp, grid, valueT, rpath, wpath, status, flags);
 }
 
 // ======================================================================================
 // Forward primal sweep.  smem: xb[2][NE][LDA] post-lottery masses of all columns | X[LDA] | Y[LDA] |
 // g[LDA] | ms[LDA] (int) | st[LDA+4] (int) | bar[2].   kdpart: [P][NE*NT/32].
 // ======================================================================================
+// (pol_in is not __restrict__: in k_primal_ds_both it is the policy the backward sweep of the same kernel wrote)
 template <int NE, int R, int NT>
-__global__ void __launch_bounds__(NT, 1)
-k_forward_primal_ds(const Consts<NE> M, const Tape tp, const double* __restrict__ grid,
-                    const double* __restrict__ D0, const double* __restrict__ pol_in,
-                    double* __restrict__ kdpart, int* __restrict__ status) {
+__device__ __forceinline__ void fp_ds_body(const Consts<NE>& M, const Tape& tp, const double* __restrict__ grid,
+                                           const double* __restrict__ D0, const double* pol_in,
+                                           double* __restrict__ kdpart, int* __restrict__ status) {
   constexpr int LDA = NT * R, NS = LDA + 4, NW = NT / 32;
   constexpr size_t GP = (size_t)NE * LDA;
   extern __shared__ __align__(16) double smem_ds[];
@@ -307,6 +333,31 @@ k_forward_primal_ds(const Consts<NE> M, const Tape tp, const double* __restrict_
     for (int j = 0; j < R; ++j) pc[j] = pn[j];
   }
   cluster.sync();   // no CTA leaves while a peer may still be writing into it
+}
+template <int NE, int R, int NT>
+__global__ void __launch_bounds__(NT, 1)
+k_forward_primal_ds(const Consts<NE> M, const Tape tp, const double* __restrict__ grid,
+                    const double* __restrict__ D0, const double* __restrict__ pol_in,
+                    double* __restrict__ kdpart, int* __restrict__ status) {
+  fp_ds_body<NE, R, NT>(M, tp, grid, D0, pol_in, kdpart, status);
+}
+
+// ======================================================================================
+// Both primal sweeps of a linearisation in ONE launch (pipelined linearisation, hank_ctx.h): the cluster keeps its n_e
+// SMs from the first backward period to the last forward period.  With two launches the SMs of the backward sweep go to
+// the pending CTAs of the tangent sweep running next to it the moment it ends, and the forward primal sweep then waits
+// for a wave boundary (measured: no gain from the overlap at all, profiles/r02_notes.md).  CTA e reads back only the
+// policy column it wrote itself.
+// ======================================================================================
+template <int NE, int R, int NT, bool G2>
+__global__ void __launch_bounds__(NT + 32, 1)
+k_primal_ds_both(const Consts<NE> M, const Tape tp, const double* __restrict__ grid, const double* __restrict__ valueT,
+                 const double* __restrict__ rpath, const double* __restrict__ wpath, int* __restrict__ status,
+                 int* __restrict__ flags, const double* __restrict__ D0, double* __restrict__ kdpart) {
+  bp_ds_body<NE, R, NT, G2>(M, tp, grid, valueT, rpath, wpath, status, flags);
+  if (threadIdx.x >= NT) return;   // the publishing warp is done (exited warps do not count at later barriers)
+  __syncthreads();                 // (the invalidated barriers' bytes become the forward sweep's bracket array)
+  fp_ds_body<NE, R, NT>(M, tp, grid, D0, tp.pol, kdpart, status);
 }
 
 }  // namespace hank

@@ -216,13 +216,27 @@ k_backward_tangent_tma(const Consts<NE> M, const Tape tp, int K, int Kp, int S, 
 // smem: ring[NE][bw chunk] | kb[2][L][LDA] | drw[2][2L] | full[NE].   Fits for NE * 52 * LDA + 16 L LDA <= ~225 KB
 // (500 x 7 with up to 4 lanes); other shapes keep the kernel above.  No seeded V̇ (single-step callers).
 // ======================================================================================
+// Pipelined linearisation: chunk (t, e) of the backward tape may be fetched once the primal sweep running next to this
+// kernel has published P - t completed periods for income state e (k_backward_primal_ds).  `seen` caches the last
+// count read: the primal runs ~4x faster per period than a wave of this sweep, so a handful of polls cover a sweep.
+__device__ __forceinline__ void wait_tape_flag(const int* flag, int need, int& seen) {
+  if (seen >= need) return;
+  const long long t0 = clock64();
+  do {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+    if (clock64() - t0 > 4000000000LL) __trap();
+  } while (seen < need);
+  asm volatile("fence.proxy.async;" ::: "memory");   // the bulk copy (async proxy) reads what the generic proxy wrote
+}
+
 template <int NE, int LDA, int L>
 constexpr size_t bt_ring_ne_smem() { return (size_t)NE * bw_chunk_bytes<LDA>() + (size_t)2 * L * LDA * 8 + (size_t)4 * L * 8 + (size_t)NE * 8 + 128; }
 
 template <int NE, int R, int NT, int L, bool SKIP>
 __global__ void __launch_bounds__(NT, 1)
 k_backward_tangent_ring_ne(const Consts<NE> M, const Tape tp, int K, int Kp, const int* __restrict__ thi,
-                           const double* __restrict__ dr, const double* __restrict__ dw, double* __restrict__ dpol) {
+                           const double* __restrict__ dr, const double* __restrict__ dw, double* __restrict__ dpol,
+                           const int* __restrict__ bpflag) {
   constexpr int LDA = NT * R, NW = NT / 32;
   constexpr int CH = (int)bw_chunk_bytes<LDA>();
   constexpr int SLOT_D = CH / 8;
@@ -250,8 +264,13 @@ k_backward_tangent_ring_ne(const Consts<NE> M, const Tape tp, int K, int Kp, con
   if (tid < 2 * L) drw[tid] = seed(tid, P - 1);
   __syncthreads();
   const unsigned char* bw_t = tp.bw + (size_t)(P - 1) * NE * CH;   // chunks of the current period
+  // (pipelined linearisation) the column this thread refills — warp w, lane 0 issues column w-1, warp 0 column NE-1 —
+  // and the primal's progress on it as last seen
+  // (with at least NE warps that is one column per issuing thread; otherwise a thread re-reads the counter every time)
+  int seen = bpflag ? 0 : 0x7fffffff;
   if (tid == 0)
     for (int e = 0; e < NE; ++e) {
+      if (bpflag) { int s0 = 0; wait_tape_flag(bpflag + e, Pfull - (P - 1), s0); }
       mbar_expect_tx(&full[e], CH);
       bulk_g2s(ring + (size_t)e * SLOT_D, bw_t + (size_t)e * CH, CH, &full[e]);
     }
@@ -316,8 +335,14 @@ k_backward_tangent_ring_ne(const Consts<NE> M, const Tape tp, int K, int Kp, con
       // (column e-1 of period t-1; for e = 0 the last column of THIS period, six columns ahead)
       if (warp == e % NW && lane == 0) {
         if (e > 0) {
-          if (t > 0) { mbar_expect_tx(&full[e - 1], CH); bulk_g2s(ring + (size_t)(e - 1) * SLOT_D, bw_t - (size_t)(NE - e + 1) * CH, CH, &full[e - 1]); }
+          if (t > 0) {
+            if (NW < NE && bpflag) seen = 0;
+            wait_tape_flag(bpflag + (e - 1), Pfull - (t - 1), seen);
+            mbar_expect_tx(&full[e - 1], CH); bulk_g2s(ring + (size_t)(e - 1) * SLOT_D, bw_t - (size_t)(NE - e + 1) * CH, CH, &full[e - 1]);
+          }
         } else if (t < P - 1) {
+          if (NW < NE && bpflag) seen = 0;
+          wait_tape_flag(bpflag + (NE - 1), Pfull - t, seen);
           mbar_expect_tx(&full[NE - 1], CH); bulk_g2s(ring + (size_t)(NE - 1) * SLOT_D, bw_t + (size_t)(NE - 1) * CH, CH, &full[NE - 1]);
         }
       }
