@@ -370,6 +370,7 @@ static int tangent_pass(hank_ctx* c, int P, int K) {
   double* dpol2 = c->d_dpol + (size_t)P * c->n_e * (size_t)K1 * c->lda;   // policy tangents of the lanes beyond the cut
   if (K1 == K) {
     RC(tangent_pass_range(c, P, K, 0, c->d_dpol));
+    c->pipe_hint = c->last_bt_mode;
     RC(join_side(c));  // the forward tangent needs the forward tape of the linearisation
     int nw = 16;
     RC(sw_forward_tangent(c, P, K, c->d_dpol, c->d_dkdpart, &nw));
@@ -387,6 +388,7 @@ static int tangent_pass(hank_ctx* c, int P, int K) {
   CK(cudaStreamWaitEvent(c->stream3, c->ev_v, 0));
   c->pass_Kp = K1;
   RC(tangent_pass_range(c, P, K1, 0, c->d_dpol));         // main wave, backward
+  c->pipe_hint = c->last_bt_mode;
   double* part2 = c->d_dkdpart + (size_t)K1 * P * 16;
   c->stream = c->stream3;
   c->pass_thi = thi + K1 / kThiGroup;
@@ -473,6 +475,9 @@ int hank_ctx_create(hank_ctx** out, int device, int n_a, int n_e, int T, const d
   { const char* nt = getenv("HANK_NO_RING_NE"); c->no_ring_ne = nt && nt[0] == '1'; }
   { const char* nt = getenv("HANK_RS_MAXK"); c->rs_max_k = nt ? atoi(nt) : 0; }
   { const char* nt = getenv("HANK_RS_RELAXED"); c->rs_relaxed = nt && nt[0] == '1'; }
+  { const char* nt = getenv("HANK_NO_RS_ST"); c->no_rs_st = nt && nt[0] == '1'; }
+  { const char* nt = getenv("HANK_NO_RS_PUSH"); c->no_rs_push = nt && nt[0] == '1'; }
+  { const char* nt = getenv("HANK_NO_RS_CE"); c->no_rs_ce = nt && nt[0] == '1'; }
   { const char* nt = getenv("HANK_RS_NO_MULTI"); c->rs_no_multi = nt && nt[0] == '1'; }
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   {
@@ -511,7 +516,7 @@ int hank_ctx_create(hank_ctx** out, int device, int n_a, int n_e, int T, const d
   RC(dalloc(c, &c->d_status, 4));
   RC(dalloc(c, &c->d_bpflag, 16));
   CK(cudaMemset(c->d_bpflag, 0, 16 * sizeof(int)));
-  c->no_pipe = getenv("HANK_NO_PIPE") != nullptr;
+  { const char* nt = getenv("HANK_NO_PIPE"); c->no_pipe = nt && nt[0] == '1'; }
   CK(cudaMemset(c->d_status, 0, 4 * sizeof(int)));
   CK(cudaMallocHost((void**)&c->h_status, 4 * sizeof(int)));
   const size_t n = (size_t)4 * c->P;
@@ -947,7 +952,7 @@ int hank_ks_linearize_dev(hank_ctx* c, const double* x, const double* Z, double*
   // (hank_ctx.h): the backward primal sweep goes there too, and a backward tangent sweep of the one-CTA ring kernel
   // launched next may run alongside it, following its progress counters; everything else joins first (join_bp).
   cudaStream_t main_stream = c->stream;
-  const bool pipe = !c->no_overlap && !c->no_pipe && c->stream2 && c->d_bpflag;
+  const bool pipe = !c->no_overlap && !c->no_pipe && c->stream2 && c->d_bpflag && c->pipe_hint > 0;
   bool fused = false;
   if (pipe) {
     k_fill_rho<<<nblk(P), 256, 0, main_stream>>>(c->d_r, P, c->tape.rho);
@@ -956,9 +961,9 @@ int hank_ks_linearize_dev(hank_ctx* c, const double* x, const double* Z, double*
     CK(cudaStreamWaitEvent(c->stream2, c->ev_bp, 0));
     c->stream = c->stream2;
     int rcb = -1;
-    // a many-lane tangent pass followed the last linearisation (pipe_hint): both primal sweeps in one launch, so that the
-    // cluster's SMs are not taken by that pass's pending CTAs between the two sweeps
-    if (c->pipe_hint) {
+    // a multi-wave tangent pass followed the last linearisation (pipe_hint 2): both primal sweeps in one launch, so that
+    // the cluster's SMs are not taken by that pass's pending CTAs between the two sweeps
+    if (c->pipe_hint == 2) {
       rcb = sw_primal_both(c, P, c->d_valueT, c->d_r, c->d_w, c->d_D0);
       if (rcb == 0) {
         fused = true;

@@ -26,7 +26,10 @@ struct hank_ctx {
   int* d_bpflag = nullptr;
   cudaEvent_t ev_bps = nullptr, ev_bpd = nullptr, next_launch_ev = nullptr;
   bool bp_pending = false, bp_flags = false, bp_pipe_req = false, no_pipe = false;
-  bool pipe_hint = false;   // the last tangent pass followed a primal sweep in flight: fuse the next linearisation's primal sweeps
+  // What the last backward tangent launch says about the next linearisation (pipe_hint, set by tangent_pass from the main
+  // wave's last_bt_mode): 0 serial order; 1 backward primal on the side stream with progress counters, tangent sweep next
+  // to it; 2 the same with both primal sweeps in one launch (k_primal_ds_both)
+  int last_bt_mode = 0, pipe_hint = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int smem_max = 0, sm_count = 0;
 
@@ -86,6 +89,7 @@ struct hank_ctx {
   bool no_skip = false;          // HANK_NO_SKIP=1: unit-seed Jacobian lanes sweep all periods
   bool no_ring_ne = false;       // HANK_NO_RING_NE=1: backward tangent always through the runtime-sized ring
   bool no_rowsplit = false;      // HANK_NO_ROWSPLIT=1: never split a lane group's rows over a cluster
+  bool no_rs_st = false, no_rs_push = false, no_rs_ce = false;   // HANK_NO_RS_ST / _PUSH / _CE=1: one-lane row-split sweeps without the st.async / bulk-push / thread-per-(e,row) kernels
   bool rs_relaxed = false;       // HANK_RS_RELAXED=1: relaxed cluster hand-shakes in the row-split kernels (racy; A/B only)
   bool rs_no_multi = false;      // HANK_RS_NO_MULTI=1: no multi-lane row-split clusters (mid lane counts run one CTA per lane)
   int rs_max_k = 0;              // HANK_RS_MAXK: lane count up to which 1-lane row-split clusters are used (0: sm_count / NC)

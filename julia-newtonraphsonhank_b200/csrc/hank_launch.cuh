@@ -314,10 +314,16 @@ static int bt_launch(hank_ctx* c, int P, int K, const double* dr, const double* 
       // next to a backward primal sweep still in flight (pipelined linearisation): start once its CTAs are resident
       // and follow its progress counters; everything after this sweep is ordered behind the primal's completion
       const bool pipe = c->bp_pending && c->bp_flags;
-      c->pipe_hint = true;   // (a pass of this kind can follow a primal sweep in flight: worth fusing the next one's)
+      // A pass of this kind can follow a primal sweep in flight.  Whether the NEXT linearisation should be pipelined
+      // (tangent_pass turns this into pipe_hint) depends on what bounds the step.  More than one wave of CTAs: the
+      // backward tangent sweep is the long pole — overlap it with the backward primal, and launch both primal sweeps as
+      // one kernel so that the cluster keeps its SMs in between (2).  About one wave: the forward primal cannot start
+      // until tangent CTAs leave; overlapping the backward primal moves everything 0.7 ms earlier (1).  Seed-horizon
+      // passes (sorted, short) and passes that leave SMs free anyway are bounded by backward primal -> forward primal
+      // -> forward tangent: serial order, no counters, no extra stream hops (0; measured 0.1 ms slower otherwise).
+      c->last_bt_mode = c->pass_thi ? 0 : grid > c->sm_count ? 2 : grid > c->sm_count - 2 * NE ? 1 : 0;
       const int* flags = pipe ? c->d_bpflag : nullptr;
-      static const bool nowait = getenv("HANK_PIPE_NOWAIT") != nullptr;
-      if (pipe && !nowait) { int rcw = cuda_check(c, cudaStreamWaitEvent(c->stream, c->ev_bps, 0), "cudaStreamWaitEvent(ev_bps)"); if (rcw) return rcw; }
+      if (pipe) { int rcw = cuda_check(c, cudaStreamWaitEvent(c->stream, c->ev_bps, 0), "cudaStreamWaitEvent(ev_bps)"); if (rcw) return rcw; }
       else { int rcw = join_bp(c); if (rcw) return rcw; }
       auto launch = [&]() -> int {
         if (c->pass_thi)
@@ -398,8 +404,8 @@ int Sweeps<NE>::backward_tangent(hank_ctx* c, int P, int K, const double* dr, co
   // single-step callers (hank_egm_step, hank_vfi) seed V̇ and read it back: one-CTA kernels only
   const bool allow_rs = dvalT == nullptr && dvf == nullptr;
   TangentCfg cfg = tangent_cfg<NE>(c, K, allow_rs);
+  c->last_bt_mode = 0;
   if (cfg.NC > 0) {
-    c->pipe_hint = false;
     { int rcw = join_bp(c); if (rcw) return rcw; }
     const int rc = Sweeps<NE>::backward_tangent_rs(c, cfg.NC, cfg.NT, cfg.L, cfg.GC, P, K, dr, dw, dpol);
     if (rc >= 0) return rc;

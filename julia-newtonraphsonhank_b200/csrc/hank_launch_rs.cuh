@@ -80,7 +80,7 @@ static int bt_rs_launch(hank_ctx* c, int P, int K, const double* dr, const doubl
   const size_t slot = (size_t)GC * rs_bw_col_bytes<NT>();
   // one lane, a whole period per exchange: the push kernels (hank_tangent_rowsplit.cuh) where their buffers fit
   if constexpr (L == 1 && GC == NE && LA == 0 && NE * NT + 64 <= 1024) {
-    static const bool no_push = getenv("HANK_NO_RS_PUSH") != nullptr, no_st = getenv("HANK_NO_RS_ST") != nullptr;
+    const bool no_push = c->no_rs_push, no_st = c->no_rs_st;
     if constexpr (NT == 64 && NC <= 8) {   // every thread sends its own value with st.async
       const int Ss = rs_ring_slots(c, rs_bw_st_smem<NE, NC, NT>(0), rs_bw_st_slot<NE, NC, NT>(), 2, 6);
       if (!no_push && !no_st && Ss >= 2) {
@@ -121,7 +121,7 @@ static int ft_rs_launch(hank_ctx* c, int P, int K, const double* dpol, double* d
   const size_t slot = (size_t)GC * rs_fw_col_bytes<NT, L>();
   // one lane, a whole period per exchange: a thread per (income state, row) instead of per row (hank_tangent_rowsplit.cuh)
   if constexpr (L == 1 && GC == NE && LA == 0 && NE * NT + 64 <= 1024) {
-    static const bool no_push = getenv("HANK_NO_RS_PUSH") != nullptr, no_st = getenv("HANK_NO_RS_ST") != nullptr;
+    const bool no_push = c->no_rs_push, no_st = c->no_rs_st;
     if constexpr (NT == 64 && NC <= 8) {   // every thread sends its own masses with st.async
       const int Ss = rs_ring_slots(c, rs_fw_st_smem<NE, NC, NT>(0), rs_fw_st_slot<NE, NC, NT>(), 2, 6);
       if (!no_push && !no_st && Ss >= 2) {
@@ -145,7 +145,7 @@ static int ft_rs_launch(hank_ctx* c, int P, int K, const double* dpol, double* d
                                (const double*)c->d_zero, dpol, pd_rs ? 1 : 0, dkdpart);
       if (rc >= 0) return rc;
     }
-    static const bool no_ce = getenv("HANK_NO_RS_CE") != nullptr;
+    const bool no_ce = c->no_rs_ce;
     const int Sc = rs_ring_slots(c, rs_fw_ce_smem<NE, NT>(0), slot + 16, 2, 6);
     if (!no_ce && Sc >= 2) {
       int rc = ensure_tape_rs(c, P, NT, true);

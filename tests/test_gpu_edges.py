@@ -59,7 +59,9 @@ def test_lane_counts_and_shapes(n_a, n_e, K):
 @pytest.mark.parametrize("switch,n_a,K", [("HANK_NO_TMA", 500, 9), ("HANK_NO_TMA", 1000, 5), ("HANK_NO_CLUSTER", 500, 3),
                                           ("HANK_NO_DSMEM", 500, 3), ("HANK_NO_DSMEM", 1000, 2), ("HANK_NO_WIDE", 500, 700),
                                           ("HANK_NO_OVERLAP", 500, 5), ("HANK_NO_ROWSPLIT", 500, 5),
-                                          ("HANK_NO_ROWSPLIT", 1000, 3), ("HANK_NO_ROWSPLIT", 2000, 2)])
+                                          ("HANK_NO_ROWSPLIT", 1000, 3), ("HANK_NO_ROWSPLIT", 2000, 2),
+                                          ("HANK_NO_RS_ST", 500, 3), ("HANK_NO_RS_PUSH", 500, 3), ("HANK_NO_RS_ST", 200, 2),
+                                          ("HANK_NO_PIPE", 500, 700)])
 def test_fallback_kernels_agree_with_oracle(switch, n_a, K, monkeypatch):
     """The A/B switches read at hank_ctx_create select the fallback kernels (register-prefetch tangents,
     single-CTA and global-exchange primal sweeps, no 6-lane shape, no side stream): same parity bar."""
@@ -207,6 +209,37 @@ def test_side_stream_overlap_does_not_change_results(monkeypatch):
     F2 = blk2.linearize(x0, Z); JV2 = blk2.jvp(V)
     blk2.close()
     assert np.array_equal(F, F2) and np.array_equal(JV, JV2)
+
+
+@pytest.mark.parametrize("K", [700, 592])
+def test_pipelined_linearisation_does_not_change_results(K, monkeypatch):
+    """After a many-lane pass, hank_ks_linearize puts the backward primal sweep on the side stream and lets the next
+    many-lane backward tangent sweep follow its per-period progress counters; after a multi-wave pass (K = 700) both
+    primal sweeps are one launch (k_primal_ds_both), after a one-wave pass (K = 592) two.  Three linearisations at DIFFERENT points (a tangent sweep that ran ahead of the primal would
+    read the previous point's tape), many-lane and few-lane passes in between; HANK_NO_PIPE=1 serialises.  Same
+    kernels per point, same results bit for bit."""
+    rng = np.random.default_rng(17)
+    def run():
+        blk, x0, Z, P = _ks_block("ss_500x7_T300.npz")
+        V = rng.standard_normal((K, 4 * P)); V1 = V[:3]
+        out = []
+        for i in range(3):
+            x = x0 * (1.0 + 1e-3 * i * np.sin(np.arange(x0.size)))
+            out.append(blk.linearize(x, Z)); out.append(blk.jvp(V))
+            if i == 1:
+                out.append(blk.jvp(V1))                  # a few-lane (row-split) pass at the same linearisation
+        out.append(blk.linearize(x0, Z)); out.append(blk.jvp(V1))   # few lanes straight after a (fused) linearisation
+        out.append(blk.policies(0)); out.append(blk.dist(P))
+        blk.close()
+        return out
+    a = run()
+    rng = np.random.default_rng(17)
+    monkeypatch.setenv("HANK_NO_PIPE", "1")
+    b = run()
+    assert len(a) == len(b)
+    for u, v in zip(a, b):
+        assert np.array_equal(u, v)
+    assert not np.array_equal(a[0], a[2])                # (the points really differ)
 
 
 def test_jacobian_seed_horizons_do_not_change_columns(monkeypatch):
