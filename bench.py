@@ -399,7 +399,10 @@ def main():
                 "kernel_ms_per_launch": per,
                 "frac_by_kernel": {k: alg / (per[k] * 1e-3) / 1e9 / peak for k in ("backward_tangent", "forward_tangent")},
                 "sweep_pair_GBps": 2 * alg / ((per["backward_tangent"] + per["forward_tangent"]) * 1e-3) / 1e9,
-                "us_per_period": {k: 1e3 * v / P for k, v in per.items() if v}}
+                "us_per_period": {k: 1e3 * v / P for k, v in per.items() if v},
+                "note": "event-timed on the launching stream inside the timed steps; with the pipelined linearisation "
+                        "(default; HANK_NO_PIPE=1 serialises) backward_primal is the fused launch of both primal sweeps and "
+                        "the backward tangent's time contains the late start of the CTAs displaced by the primal cluster"}
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
