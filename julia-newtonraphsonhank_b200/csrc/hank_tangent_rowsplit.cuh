@@ -1216,22 +1216,30 @@ k_forward_tangent_rs_st(const Consts<NE> M, const unsigned char* __restrict__ ta
     int cnt_next = (tid == 0 && P > 0) ? __ldg(cnt + rank) : 0;
     double Dd = 0.0;
     Cursor sl_c;
+    // Software pipeline: the tape values of period t+1 are fetched (and the slot handed back) and the <p, Ḋ> partial of
+    // period t-1 is reduced while the pushes of period t travel — the warp would only wait there.
+    double pd = 0.0, om = 0.0, dco = 0.0, Dn = 0.0, pv = 0.0, kprev = 0.0;
+    int s0 = 0, s1 = 0, s2 = 0, inf = -1;
+    auto fetch = [&](double& pd_, double& om_, double& dco_, double& Dn_, double& pv_, int& s0_, int& s1_, int& s2_, int& inf_) {
+      const double* sl = ring + (size_t)sl_c.i * SLOTD;
+      mbar_wait(&full[sl_c.i], sl_c.par);
+      pd_ = sl[PD_OFF + e * NT + row];
+      om_ = sl[e * COLD + FW_OM * NT + row]; dco_ = sl[e * COLD + FW_DCO * NT + row];
+      Dn_ = sl[e * COLD + FW_D * NT + row]; pv_ = sl[e * COLD + FW_P * NT + row];
+      const int* sst = reinterpret_cast<const int*>(sl + e * COLD + ST_OFF) + row + 1;
+      s0_ = sst[0]; s1_ = sst[1]; s2_ = sst[2];
+      inf_ = reinterpret_cast<const int*>(sl + IN_OFF)[e * NT + row];
+      __syncwarp();
+      if (lane == 0) mbar_arrive_local(&empty[sl_c.i]);   // everything this warp needs of the slot is in registers
+      sl_c.next(S);
+    };
+    if (P > 0) fetch(pd, om, dco, Dn, pv, s0, s1, s2, inf);
     for (int t = 0; t < P; ++t) {
       const int b = t & 1;
       if (tid == 0) {
         mbar_expect_tx(&xbar[b], (uint32_t)(cnt_next + NC) * 8u);
         if (t + 1 < P) cnt_next = __ldg(cnt + (size_t)(t + 1) * NC + rank);
       }
-      const double* sl = ring + (size_t)sl_c.i * SLOTD;
-      mbar_wait(&full[sl_c.i], sl_c.par);
-      const double pd = sl[PD_OFF + e * NT + row];
-      const double om = sl[e * COLD + FW_OM * NT + row], dco = sl[e * COLD + FW_DCO * NT + row];
-      const double Dn = sl[e * COLD + FW_D * NT + row], pv = sl[e * COLD + FW_P * NT + row];
-      const int* sst = reinterpret_cast<const int*>(sl + e * COLD + ST_OFF) + row + 1;
-      const int s0 = sst[0], s1 = sst[1], s2 = sst[2];
-      const int inf = reinterpret_cast<const int*>(sl + IN_OFF)[e * NT + row];
-      __syncwarp();
-      if (lane == 0) mbar_arrive_local(&empty[sl_c.i]);   // everything this warp needs of the slot is in registers
       // ---- the masses of this source go to the owners of their destination rows
       const double xd = fma(om, Dd, dco * pd);
       const uint32_t dx = (uint32_t)inf & 255u, dy = ((uint32_t)inf >> 8) & 255u;
@@ -1240,28 +1248,36 @@ k_forward_tangent_rs_st(const Consts<NE> M, const unsigned char* __restrict__ ta
       if (dy < (uint32_t)NC) st_async_f64(map_to_cta(xoff + (uint32_t)XYD * 8u, dy), Dd - xd, map_to_cta(xbar_s + 8u * (uint32_t)b, dy));
       if (tid < NC) st_async_f64(tok_dst + (uint32_t)(b * NC) * 8u, 0.0, tok_bar + 8u * (uint32_t)b);
       double kacc = pd * Dn;
+      // ---- while they travel: last period's <p, Ḋ> partial of the warp, next period's tape values
+      if (t > 0) {
+        const double s = warp_sum(kprev);
+        if (lane == 0) red[((t - 1) & 1) * NWC + warp] = s;
+      }
+      const int c0 = s0, c1 = s1, c2 = s2;
+      const double pvc = pv;
+      if (t + 1 < P) fetch(pd, om, dco, Dn, pv, s0, s1, s2, inf);
       // ---- the sources of this destination row, now in this CTA's buffer
       mbar_wait_cluster(&xbar[b], (uint32_t)((t >> 1) & 1));
       const double* xb = xy + (size_t)(b * 2) * XYD + e * LDA;
       const double* yb = xb + XYD;
-      const int n1 = s1 - s0, n2 = s2 - s1;
+      const int n1 = c1 - c0, n2 = c2 - c1;
       double acc = 0.0;                         // 0 + x0 + y0 + x1 + y1 + the rest of x, then of y: gather_row's order
-      if (n1 > 0) acc = xb[s0];
-      if (n2 > 0) acc += yb[s1];
-      if (n1 > 1) acc += xb[s0 + 1];
-      if (n2 > 1) acc += yb[s1 + 1];
+      if (n1 > 0) acc = xb[c0];
+      if (n2 > 0) acc += yb[c1];
+      if (n1 > 1) acc += xb[c0 + 1];
+      if (n2 > 1) acc += yb[c1 + 1];
       const int mx = max(n1, n2) - 2;
       if (__any_sync(0xffffffffu, mx > 0)) {
         constexpr int kSerial = 8;
         if (mx > 0 && mx <= kSerial) {
-          for (int q = s0 + 2; q < s1; ++q) acc += xb[q];
-          for (int q = s1 + 2; q < s2; ++q) acc += yb[q];
+          for (int q = c0 + 2; q < c1; ++q) acc += xb[q];
+          for (int q = c1 + 2; q < c2; ++q) acc += yb[q];
         }
         unsigned bal = __ballot_sync(0xffffffffu, mx > kSerial);
         while (bal) {                            // long ranges (the mass at the borrowing constraint): the whole warp
           const int src = __ffs(bal) - 1;
           bal &= bal - 1;
-          const int b0 = __shfl_sync(0xffffffffu, s0, src), b1 = __shfl_sync(0xffffffffu, s1, src), b2 = __shfl_sync(0xffffffffu, s2, src);
+          const int b0 = __shfl_sync(0xffffffffu, c0, src), b1 = __shfl_sync(0xffffffffu, c1, src), b2 = __shfl_sync(0xffffffffu, c2, src);
           double v = 0.0;
           for (int q = b0 + 2 + lane; q < b1; q += 32) v += xb[q];
           for (int q = b1 + 2 + lane; q < b2; q += 32) v += yb[q];
@@ -1272,7 +1288,7 @@ k_forward_tangent_rs_st(const Consts<NE> M, const unsigned char* __restrict__ ta
       // ---- Markov mix across the income states of the row and <p_t, Ḋ_t>
       mix[e * NT + row] = acc;
       named_bar_sync(2, NTC);
-      if (t > 0 && tid == 0 && lane0 < K) {
+      if (t > 0 && tid == 0 && lane0 < K) {   // (every warp wrote its partial of period t-1 before this barrier)
         double s = 0.0;
 #pragma unroll
         for (int w = 0; w < NWC; ++w) s += red[((t - 1) & 1) * NWC + w];
@@ -1282,10 +1298,11 @@ k_forward_tangent_rs_st(const Consts<NE> M, const unsigned char* __restrict__ ta
 #pragma unroll
       for (int e1 = 0; e1 < NE; ++e1) d = fma(pic[e1], mix[e1 * NT + row], d);
       Dd = d;
-      kacc = fma(pv, d, kacc);
-      const double s = warp_sum(kacc);
-      if (lane == 0) red[(t & 1) * NWC + warp] = s;
-      sl_c.next(S);
+      kprev = fma(pvc, d, kacc);
+    }
+    if (P > 0) {
+      const double s = warp_sum(kprev);
+      if (lane == 0) red[((P - 1) & 1) * NWC + warp] = s;
     }
     named_bar_sync(3, NTC);
     if (tid == 0 && lane0 < K && P > 0) {
@@ -1368,6 +1385,22 @@ k_backward_tangent_rs_st(const Consts<NE> M, const Tape tp, const unsigned char*
     double rho = __ldg(tp.rho + (P > 0 ? P - 1 : 0));
     double drn = on ? __ldg(dr + (size_t)lane0 * Pfull + P - 1) : 0.0, dwn = on ? __ldg(dw + (size_t)lane0 * Pfull + P - 1) : 0.0;
     Cursor sl_c;
+    // (software pipeline as in k_forward_tangent_rs_st: next period's tape values are fetched while the pushes travel)
+    double a1 = 0.0, kr = 0.0, cA = 0.0, cB = 0.0, E1 = 0.0, vf = 0.0;
+    int i0 = 0;
+    unsigned mk = 0u;
+    auto fetch = [&]() {
+      const double* sl = ring + (size_t)sl_c.i * SLOTD + e * COLD + row;
+      mbar_wait(&full[sl_c.i], sl_c.par);
+      a1 = sl[BW_A1 * NT]; kr = sl[BW_KR * NT];
+      cA = sl[BW_CA * NT]; cB = sl[BW_CB * NT]; E1 = sl[BW_E1 * NT]; vf = sl[BW_VF * NT];
+      i0 = reinterpret_cast<const int*>(sl - row + BW_NF * NT)[row];
+      mk = (unsigned)reinterpret_cast<const int*>(ring + (size_t)sl_c.i * SLOTD + IN_OFF)[e * NT + row];
+      __syncwarp();
+      if (lane == 0) mbar_arrive_local(&empty[sl_c.i]);
+      sl_c.next(S);
+    };
+    if (P > 0) fetch();
     for (int it = 0; it < P; ++it) {
       const int t = P - 1 - it, b = it & 1;
       const double rho_t = rho, drl = drn, dwl = dwn;
@@ -1387,31 +1420,26 @@ k_backward_tangent_rs_st(const Consts<NE> M, const Tape tp, const unsigned char*
 #pragma unroll
       for (int e2 = 0; e2 < NE; ++e2) ev = fma(pir[e2], mixv[e2 * NT + row], ev);
       // ---- k̇ of this (row, income state), sent to the owners of the rows that interpolate on it
-      const double* sl = ring + (size_t)sl_c.i * SLOTD + e * COLD + row;
-      mbar_wait(&full[sl_c.i], sl_c.par);
-      const double a1 = sl[BW_A1 * NT], kr = sl[BW_KR * NT];
-      const double cA = sl[BW_CA * NT], cB = sl[BW_CB * NT], E1 = sl[BW_E1 * NT], vf = sl[BW_VF * NT];
-      const int i0 = reinterpret_cast<const int*>(sl - row + BW_NF * NT)[row];
-      unsigned mk = (unsigned)reinterpret_cast<const int*>(ring + (size_t)sl_c.i * SLOTD + IN_OFF)[e * NT + row];
-      __syncwarp();
-      if (lane == 0) mbar_arrive_local(&empty[sl_c.i]);
       const double kd = fma(a1, ev, fma(kr, drl, -(rho_t * ze) * dwl));
       const uint32_t koff = kd_s + (uint32_t)(b * KD) * 8u + mine_off;
-      while (mk) {
-        const uint32_t d = (uint32_t)__ffs((int)mk) - 1u;
-        mk &= mk - 1u;
+      unsigned m = mk;
+      while (m) {
+        const uint32_t d = (uint32_t)__ffs((int)m) - 1u;
+        m &= m - 1u;
         st_async_f64(map_to_cta(koff, d), kd, map_to_cta(xbar_s + 8u * (uint32_t)b, d));
       }
       if (tid < NC) st_async_f64(tok_dst + (uint32_t)(b * NC) * 8u, 0.0, tok_bar + 8u * (uint32_t)b);
+      const double cAc = cA, cBc = cB, E1c = E1, vfc = vf;
+      const int i0c = i0;
+      if (it + 1 < P) fetch();
       // ---- ṗ and V̇ from k̇ at the two knots
       mbar_wait_cluster(&xbar[b], (uint32_t)((it >> 1) & 1));
       const double* kb = kdb + (size_t)b * KD + e * LDA;
-      const double k0 = live ? kb[i0] : 0.0;
-      const double k1 = live ? kb[i0 + 1] : 0.0;
-      const double pd = fma(cA, k0, cB * k1);
+      const double k0 = live ? kb[i0c] : 0.0;
+      const double k1 = live ? kb[i0c + 1] : 0.0;
+      const double pd = fma(cAc, k0, cBc * k1);
       __stcs(dpol + (((size_t)t * ncl + cluster) * NC + rank) * (size_t)(NE * NT) + e * NT + row, pd);
-      Vd = fma(vf, fma(ze, dwl, -pd), E1 * drl);
-      sl_c.next(S);
+      Vd = fma(vfc, fma(ze, dwl, -pd), E1c * drl);
     }
   }
   __syncwarp();
