@@ -230,6 +230,9 @@ def test_pipelined_linearisation_does_not_change_results(K, monkeypatch):
                 out.append(blk.jvp(V1))                  # a few-lane (row-split) pass at the same linearisation
         out.append(blk.linearize(x0, Z)); out.append(blk.jvp(V1))   # few lanes straight after a (fused) linearisation
         out.append(blk.policies(0)); out.append(blk.dist(P))
+        out.append(blk.jvp(V))                                       # many lanes again: the next linearisation is pipelined,
+        out.append(blk.linearize(x0 * (1.0 + 2e-3 * np.cos(np.arange(x0.size))), Z))
+        out.append(blk.jacobian_columns(1, 4 * P + 1))               # and a seed-horizon pass (+ overflow lanes) follows it
         blk.close()
         return out
     a = run()
